@@ -1,0 +1,573 @@
+// bh_kernels.cuh -- hand-written sm_100a kernels of the Barnes-Hut step.
+//
+// One kernel per stage of the reference's step (GPUBarnesHutNBodySimulation.java:258-263):
+//   bbox_kernel       <- kernels/nbody/boundingbox.cl
+//   build_kernel      <- kernels/nbody/buildtree.cl
+//   summarize_kernel  <- kernels/nbody/summarizetree.cl
+//   sort_kernel       <- kernels/nbody/sort.cl
+//   force_kernel      <- kernels/nbody/calculateforce.cl
+//   integrate_kernel  <- kernels/nbody/integrate.cl
+// They reproduce the reference's *results* (see DESIGN.md for the parity classes),
+// not its code: the data layout, work decomposition and synchronisation are
+// designed for B200.
+//
+// HBM layout (N bodies, M = number of nodes, NC = M - N + 1 cell slots):
+//   node4  float4[M+1]   {x, y, z, mass}; bodies 0..N-1, cells N..M, root = M.
+//                        During build a cell holds its geometric centre and
+//                        mass = -1; summarise overwrites it with {COM, mass}.
+//   velacc float4[2N]    {vx,vy,vz,0},{ax,ay,az,0} per body: one 32-byte sector.
+//   child  int[8*NC]     child[(cell-N)*8 + k]; -1 empty, -2 locked, <N body, >=N cell
+//   octet  float4[8*NC]  copy of the node4 records of a cell's (compacted)
+//                        children, written by summarise: the force walk reads a
+//                        cell's children as one 128-byte line.
+//   start, count int[NC] `start` and `bodyCount` of the reference; count doubles
+//                        as the "summarised" flag (-1 = not yet).
+//   sorted int[N]        bodies in tree (DFS) order.
+//
+// Floating-point policy (DESIGN.md "FMA policy"): every source-level x*y+z of the
+// reference is one fmaf, everything else a separately rounded IEEE operation,
+// spelled with intrinsics so that nvcc cannot re-associate.  The oracle's
+// fma_policy=1 is the same policy, which makes every stage except the rsqrt in
+// the force kernel bit-reproducible on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bh {
+
+constexpr int kMaxDepth = 64;       // MAXDEPTH, calculateforce.cl:12
+constexpr int kLock = -2;           // LOCK, buildtree.cl:8
+constexpr int kSpinBudget = 1 << 24;  // polls before a device-side wait gives up (error = 2)
+
+struct Scalars {
+    int step;         // init -1 (GPUBH:165)
+    int blockCount;   // last-block-done ticket of bbox_kernel
+    float radius;
+    int maxDepth;     // init 1, running max (buildtree.cl:199)
+    int bottom;
+    int error;
+    int pad0, pad1;
+    unsigned long long interactions;
+    unsigned long long opens;
+};
+
+// ---- memory-model helpers -------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(int *p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int octant(float cx, float cy, float cz, float bx, float by, float bz) {
+    // buildtree.cl:65-68: strict <, ties go to the low octant
+    return (cx < bx ? 1 : 0) + (cy < by ? 2 : 0) + (cz < bz ? 4 : 0);
+}
+
+// ---- 1. bounding box --------------------------------------------------------
+// boundingbox.cl: min/max over bodies, root cell, per-step resets.  Warp-shuffle
+// reduction, one shared-memory hop per block, last-block-done combine.
+constexpr int kBboxThreads = 512;
+
+__device__ __forceinline__ void warp_minmax(float &mnx, float &mny, float &mnz, float &mxx, float &mxy, float &mxz) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+}
+
+__global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__ node4, int *__restrict__ child,
+                                                            int *__restrict__ start, int *__restrict__ count,
+                                                            float *__restrict__ partials, Scalars *__restrict__ sc,
+                                                            int n, int m) {
+    __shared__ float red[6][kBboxThreads / 32];
+    __shared__ bool isLast;
+    const float4 seed = node4[0];  // boundingbox.cl:44-58: every lane starts from body 0
+    float mnx = seed.x, mny = seed.y, mnz = seed.z, mxx = seed.x, mxy = seed.y, mxz = seed.z;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = node4[i];
+        mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x);
+        mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
+        mnz = fminf(mnz, p.z); mxz = fmaxf(mxz, p.z);
+    }
+    warp_minmax(mnx, mny, mnz, mxx, mxy, mxz);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mnz;
+        red[3][warp] = mxx; red[4][warp] = mxy; red[5][warp] = mxz;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int nw = kBboxThreads / 32;
+        mnx = red[0][lane % nw]; mny = red[1][lane % nw]; mnz = red[2][lane % nw];
+        mxx = red[3][lane % nw]; mxy = red[4][lane % nw]; mxz = red[5][lane % nw];
+        warp_minmax(mnx, mny, mnz, mxx, mxy, mxz);
+        if (lane == 0) {
+            float *out = partials + 6 * blockIdx.x;
+            out[0] = mnx; out[1] = mny; out[2] = mnz; out[3] = mxx; out[4] = mxy; out[5] = mxz;
+            __threadfence();
+            // atomicInc wraps to 0 at gridDim-1: blockCount is back to 0 for the next step (boundingbox.cl:181)
+            isLast = (atomicInc(reinterpret_cast<unsigned *>(&sc->blockCount), gridDim.x - 1) == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!isLast || warp != 0) return;
+    __threadfence();
+    mnx = seed.x; mny = seed.y; mnz = seed.z; mxx = seed.x; mxy = seed.y; mxz = seed.z;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+        const float *in = partials + 6 * b;
+        mnx = fminf(mnx, __ldcg(in + 0)); mny = fminf(mny, __ldcg(in + 1)); mnz = fminf(mnz, __ldcg(in + 2));
+        mxx = fmaxf(mxx, __ldcg(in + 3)); mxy = fmaxf(mxy, __ldcg(in + 4)); mxz = fmaxf(mxz, __ldcg(in + 5));
+    }
+    warp_minmax(mnx, mny, mnz, mxx, mxy, mxz);
+    if (lane < 8) child[8 * (size_t)(m - n) + lane] = -1;  // boundingbox.cl:193
+    if (lane == 0) {
+        // boundingbox.cl:171-195
+        const float rx = __fmul_rn(0.5f, __fadd_rn(mnx, mxx));
+        const float ry = __fmul_rn(0.5f, __fadd_rn(mny, mxy));
+        const float rz = __fmul_rn(0.5f, __fadd_rn(mnz, mxz));
+        sc->radius = __fmul_rn(0.5f, fmaxf(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny)), __fsub_rn(mxz, mnz)));
+        sc->bottom = m;
+        node4[m] = make_float4(rx, ry, rz, -1.0f);
+        start[m - n] = 0;
+        count[m - n] = -1;
+        sc->step = sc->step + 1;
+    }
+}
+
+// ---- 2. tree build ------------------------------------------------------------
+// buildtree.cl: concurrent insertion; a child slot is locked by CAS to -2 while a
+// leaf is split, the finished sub-tree is published after a device fence.  The
+// tree *shape* is a function of the positions and the root box only; cell
+// numbers depend on the allocation race (as in the reference).  Bodies are
+// visited through `order` (previous step's sorted[] = spatial order) when given.
+constexpr int kBuildThreads = 256;
+
+__global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict__ node4, int *child,
+                                                              int *__restrict__ start, int *__restrict__ count,
+                                                              const int *__restrict__ order, Scalars *sc, int n, int m) {
+    const float radius = sc->radius;
+    const float4 root = node4[m];
+    int localMaxDepth = 1;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int body = order ? order[i] : i;
+        const float4 p = node4[body];
+        int node = m, depth = 1;
+        float r = radius, cx = root.x, cy = root.y, cz = root.z;
+        int path = octant(cx, cy, cz, p.x, p.y, p.z);
+        int spins = 0;
+        for (;;) {
+            int *slot = child + ((size_t)(node - n) * 8 + path);
+            int ch = ld_relaxed(slot);
+            while (ch >= n) {  // buildtree.cl:77-89: follow the path to a leaf slot
+                node = ch;
+                ++depth;
+                r *= 0.5f;
+                const float4 c = __ldcg(node4 + node);
+                cx = c.x; cy = c.y; cz = c.z;
+                path = octant(cx, cy, cz, p.x, p.y, p.z);
+                slot = child + ((size_t)(node - n) * 8 + path);
+                ch = ld_relaxed(slot);
+            }
+            if (ch != kLock && atomicCAS(slot, ch, kLock) == ch) {
+                if (ch == -1) {
+                    st_relaxed(slot, body);  // buildtree.cl:98-101
+                } else {
+                    // buildtree.cl:102-180: split until the two bodies separate
+                    const float4 q = node4[ch];
+                    int patch = -1, cur = node, curPath = path;
+                    bool failed = false;
+                    for (;;) {
+                        ++depth;
+                        const int cell = atomicSub(&sc->bottom, 1) - 1;
+                        if (cell <= n || depth > kMaxDepth) {  // buildtree.cl:112-119 / calculateforce.cl:69-73
+                            failed = true;
+                            break;
+                        }
+                        patch = max(patch, cell);
+                        const float ox = (curPath & 1) ? r : 0.0f;  // buildtree.cl:124-126
+                        const float oy = (curPath & 2) ? r : 0.0f;
+                        const float oz = (curPath & 4) ? r : 0.0f;
+                        r *= 0.5f;
+                        cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:134-136, left to right
+                        cy = __fadd_rn(__fsub_rn(cy, r), oy);
+                        cz = __fadd_rn(__fsub_rn(cz, r), oz);
+                        node4[cell] = make_float4(cx, cy, cz, -1.0f);
+                        start[cell - n] = -1;
+                        count[cell - n] = -1;
+                        const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
+                        const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
+                        int4 lo = make_int4(-1, -1, -1, -1), hi = lo;
+                        int *row = child + (size_t)(cell - n) * 8;
+                        reinterpret_cast<int4 *>(row)[0] = lo;
+                        reinterpret_cast<int4 *>(row)[1] = hi;
+                        if (cur != node || curPath != path) child[(size_t)(cur - n) * 8 + curPath] = cell;  // :141-146
+                        cur = cell;
+                        curPath = pPath;
+                        if (qPath != pPath) {
+                            row[qPath] = ch;    // :152
+                            row[pPath] = body;  // :169
+                            break;
+                        }
+                    }
+                    if (failed) {
+                        sc->error = 1;
+                        __threadfence();
+                        st_relaxed(slot, ch);  // give the leaf back so that nobody spins on it
+                        return;
+                    }
+                    __threadfence();          // :173 publish the sub-tree ...
+                    st_relaxed(slot, patch);  // :180 ... by replacing the lock
+                }
+                localMaxDepth = max(localMaxDepth, depth);
+                break;
+            }
+            if (ch == kLock && (++spins & 63) == 0) {
+                if (*reinterpret_cast<volatile int *>(&sc->error) != 0) return;
+                if (spins > kSpinBudget) { atomicCAS(&sc->error, 0, 2); return; }
+                __nanosleep(64);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) localMaxDepth = max(localMaxDepth, __shfl_xor_sync(0xffffffffu, localMaxDepth, o));
+    if ((threadIdx.x & 31) == 0 && localMaxDepth > 1) atomicMax(&sc->maxDepth, localMaxDepth);  // :199
+}
+
+// ---- 3. summarise ---------------------------------------------------------------
+// summarizetree.cl: bottom-up centre of mass, body counts, child compaction.
+// One thread per cell, ascending index (children have lower indices than their
+// parent); a thread waits for a child cell's count >= 0.  Children are summed
+// in octant order, which makes the result independent of timing.  Needs every
+// thread of the grid resident (grid sized by occupancy on the host).
+constexpr int kSummThreads = 256;
+
+__global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
+                                                                 float4 *__restrict__ octet, int *count, Scalars *sc,
+                                                                 int n, int m) {
+    if (sc->error != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->bottom = m;  // buildtree.cl:117
+        return;
+    }
+    const int bottom = sc->bottom;
+    const int stride = gridDim.x * blockDim.x;
+    for (int cell = bottom + blockIdx.x * blockDim.x + threadIdx.x; cell <= m; cell += stride) {
+        int *row = child + (size_t)(cell - n) * 8;
+        const int4 lo = reinterpret_cast<const int4 *>(row)[0], hi = reinterpret_cast<const int4 *>(row)[1];
+        const int in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        int out[8];
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // summarizetree.cl:77-81 compaction, octant order kept
+            if (in[k] >= 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j == used) out[j] = in[k];
+                ++used;
+            }
+        float cm = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
+        int bodies = used;  // summarizetree.cl:118
+        bool ok = true;
+        float4 *orow = octet + (size_t)(cell - n) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ch = out[k];
+            if (ch < 0) break;
+            float4 c;
+            if (ch >= n) {
+                int cnt, spins = 0;
+                while ((cnt = ld_acquire(count + (ch - n))) < 0) {
+                    if ((++spins & 255) == 0 && (spins > kSpinBudget || *reinterpret_cast<volatile int *>(&sc->error) != 0)) {
+                        ok = false;
+                        break;
+                    }
+                }
+                if (!ok) break;
+                bodies += cnt - 1;  // summarizetree.cl:98-105
+                c = __ldcg(node4 + ch);
+            } else {
+                c = node4[ch];
+            }
+            orow[k] = c;
+            cm = __fadd_rn(cm, c.w);  // summarizetree.cl:107-110
+            cx = fmaf(c.x, c.w, cx);
+            cy = fmaf(c.y, c.w, cy);
+            cz = fmaf(c.z, c.w, cz);
+        }
+        if (!ok) {
+            atomicCAS(&sc->error, 0, 2);
+            return;
+        }
+        reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
+        const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
+        __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
+        st_release(count + (cell - n), bodies);  // summarizetree.cl:160,170-172: data first, flag last
+    }
+}
+
+// ---- 4. sort ----------------------------------------------------------------------
+// sort.cl: top-down propagation of `start`, bodies written in DFS order.  One
+// thread per cell, descending index (parents first), waits for start >= 0.
+constexpr int kSortThreads = 256;
+
+__global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restrict__ child, const int *__restrict__ count,
+                                                            int *start, int *__restrict__ sorted, Scalars *sc, int n, int m) {
+    if (sc->error != 0) return;
+    const int bottom = sc->bottom;
+    const int stride = gridDim.x * blockDim.x;
+    for (int cell = m - (blockIdx.x * blockDim.x + threadIdx.x); cell >= bottom; cell -= stride) {
+        int s, spins = 0;
+        while ((s = ld_acquire(start + (cell - n))) < 0) {  // sort.cl:36-39
+            if ((++spins & 255) == 0 && (spins > kSpinBudget || *reinterpret_cast<volatile int *>(&sc->error) != 0)) {
+                atomicCAS(&sc->error, 0, 2);
+                return;
+            }
+        }
+        const int *row = child + (size_t)(cell - n) * 8;
+        const int4 lo = reinterpret_cast<const int4 *>(row)[0], hi = reinterpret_cast<const int4 *>(row)[1];
+        const int ch[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (ch[k] < 0) break;  // compacted
+            if (ch[k] >= n) {      // sort.cl:44-56
+                st_release(start + (ch[k] - n), s);
+                s += count[ch[k] - n];
+            } else {               // sort.cl:59-65
+                sorted[s++] = ch[k];
+            }
+        }
+    }
+}
+
+// ---- 5. force -------------------------------------------------------------------
+// calculateforce.cl: a vote group of VOTE consecutive sorted bodies walks the tree
+// together; a cell is used as a point mass only if *all* bodies of the group
+// are far enough (work_group_all, :145), bodies are always used.  Here one
+// hardware warp carries 32/VOTE groups through ONE shared walk: each stack entry
+// records which groups still need the cell, a group that accepted a cell simply
+// is not in the mask of that cell's children.  The set of (group, node)
+// interactions is exactly the reference's; the order in which a body sums them
+// differs (children of a popped cell are consumed before its opened children
+// are descended), which moves the fp32 sum by rounding only.
+constexpr int kForceThreads = 256;
+constexpr int kStackCap = 7 * kMaxDepth + 8;
+
+template <int VOTE, bool SLICE, bool COUNT>
+__global__ void __launch_bounds__(kForceThreads) force_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
+                                                               const int *__restrict__ child, const int *__restrict__ sorted,
+                                                               float4 *__restrict__ velacc, float4 *__restrict__ accSorted,
+                                                               Scalars *sc, int n, int m, int first, int cnt,
+                                                               float thetaMacro, float eps, float dt) {
+    __shared__ float dq[kMaxDepth];
+    __shared__ int2 stack[kForceThreads / 32][kStackCap];
+    if (sc->error != 0) return;
+    const int maxDepth = sc->maxDepth;
+    if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
+        return;
+    }
+    if (threadIdx.x == 0) {  // calculateforce.cl:52-67
+        const float radius = sc->radius;
+        float v = __fmul_rn(radius, radius);
+        if (thetaMacro > 0.0f) v = __fdiv_rn(v, thetaMacro);
+        for (int i = 0; i < maxDepth; ++i) {
+            dq[i] = __fadd_rn(v, eps);
+            v = __fmul_rn(0.25f, v);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int end = first + cnt;
+    const int base = first + (blockIdx.x * (kForceThreads / 32) + warp) * 32;
+    if (base >= end) return;
+    const int k = base + lane;
+    const bool active = k < end;
+    const int body = sorted[active ? k : base];
+    const float4 p = node4[body];
+    constexpr unsigned kFull = 0xffffffffu;
+    const int h = (VOTE == 16) ? (lane >> 4) : 0;  // which vote group of the warp this lane is in
+    const unsigned act = __ballot_sync(kFull, active);
+    int groups = (VOTE == 16) ? (((act & 0xffffu) ? 1 : 0) | ((act >> 16) ? 2 : 0)) : 1;
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    unsigned long long nInter = 0, nOpen = 0;
+    int2 *stk = stack[warp];
+    int sp = 0;
+    stk[sp++] = make_int2(m, groups);  // depth 0 in bits 2.., group mask in bits 0..1
+    while (sp > 0) {
+        const int2 e = stk[--sp];
+        __syncwarp();  // every lane has read the entry before any lane may overwrite the slot
+        const int mask = e.y & 3, d = e.y >> 2;
+        const float thr = dq[d];
+        const size_t ci = (size_t)(e.x - n) * 8;
+        const int4 lo = __ldg(reinterpret_cast<const int4 *>(child + ci));
+        const int4 hi = __ldg(reinterpret_cast<const int4 *>(child + ci) + 1);
+        const int chs[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = chs[j];
+            if (ch < 0) break;  // children are compacted (summarizetree.cl:77-81)
+            const float4 c = __ldg(octet + ci + j);
+            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            const float r2 = __fadd_rn(fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx))), eps);  // :138-143
+            int use = mask;
+            if (ch >= n) {
+                const unsigned far = __ballot_sync(kFull, r2 >= thr || !active);
+                const int all = (VOTE == 16) ? ((((far & 0xffffu) == 0xffffu) ? 1 : 0) | (((far >> 16) == 0xffffu) ? 2 : 0))
+                                             : ((far == kFull) ? 1 : 0);
+                use = mask & all;
+                const int open = mask & ~all;
+                if (open) stk[sp++] = make_int2(ch, open | ((d + 1) << 2));  // :154-163
+                if (COUNT && active && ((open >> h) & 1)) ++nOpen;
+            }
+            if ((use >> h) & 1) {  // :146-151
+                const float rinv = rsqrtf(r2);
+                const float f = __fmul_rn(__fmul_rn(__fmul_rn(c.w, rinv), rinv), rinv);
+                ax = fmaf(dx, f, ax);
+                ay = fmaf(dy, f, ay);
+                az = fmaf(dz, f, az);
+                if (COUNT && active) ++nInter;
+            }
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            nInter += __shfl_xor_sync(kFull, nInter, o);
+            nOpen += __shfl_xor_sync(kFull, nOpen, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sc->interactions, nInter);
+            atomicAdd(&sc->opens, nOpen);
+        }
+    }
+    if (!active) return;
+    if (SLICE) {
+        accSorted[k] = make_float4(ax, ay, az, 0.0f);
+    } else {
+        float4 v = velacc[2 * (size_t)body];
+        if (sc->step > 0) {  // calculateforce.cl:174-179
+            const float4 a0 = velacc[2 * (size_t)body + 1];
+            v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(ax, a0.x), dt), 0.5f));
+            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(ay, a0.y), dt), 0.5f));
+            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(az, a0.z), dt), 0.5f));
+            velacc[2 * (size_t)body] = v;
+        }
+        velacc[2 * (size_t)body + 1] = make_float4(ax, ay, az, 0.0f);  // :183-185
+    }
+}
+
+// Multi-GPU: velocity correction + acc store from the all-gathered sorted-order
+// accelerations (calculateforce.cl:174-185 for every body).
+__global__ void __launch_bounds__(256) apply_acc_kernel(const float4 *__restrict__ accSorted, const int *__restrict__ sorted,
+                                                        float4 *__restrict__ velacc, const Scalars *__restrict__ sc, int n,
+                                                        float dt) {
+    if (sc->error != 0) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int body = sorted[k];
+    const float4 a = accSorted[k];
+    if (sc->step > 0) {
+        float4 v = velacc[2 * (size_t)body];
+        const float4 a0 = velacc[2 * (size_t)body + 1];
+        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(a.x, a0.x), dt), 0.5f));
+        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(a.y, a0.y), dt), 0.5f));
+        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(a.z, a0.z), dt), 0.5f));
+        velacc[2 * (size_t)body] = v;
+    }
+    velacc[2 * (size_t)body + 1] = make_float4(a.x, a.y, a.z, 0.0f);
+}
+
+// ---- 6. integrate ---------------------------------------------------------------
+// integrate.cl:27-43
+__global__ void __launch_bounds__(256) integrate_kernel(float4 *__restrict__ node4, float4 *__restrict__ velacc,
+                                                        const Scalars *__restrict__ sc, int n, float dt) {
+    if (sc->error != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = node4[i];
+    float4 v = velacc[2 * (size_t)i];
+    const float4 a = velacc[2 * (size_t)i + 1];
+    const float dvx = __fmul_rn(__fmul_rn(a.x, dt), 0.5f);
+    const float dvy = __fmul_rn(__fmul_rn(a.y, dt), 0.5f);
+    const float dvz = __fmul_rn(__fmul_rn(a.z, dt), 0.5f);
+    v.x = __fadd_rn(v.x, dvx); v.y = __fadd_rn(v.y, dvy); v.z = __fadd_rn(v.z, dvz);
+    p.x = fmaf(v.x, dt, p.x); p.y = fmaf(v.y, dt, p.y); p.z = fmaf(v.z, dt, p.z);
+    v.x = __fadd_rn(v.x, dvx); v.y = __fadd_rn(v.y, dvy); v.z = __fadd_rn(v.z, dvz);
+    node4[i] = p;
+    velacc[2 * (size_t)i] = v;
+}
+
+// ---- host-boundary helpers: pack uploads, export logical buffers -------------------
+__global__ void pack_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                            const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                            const float *__restrict__ mass, float4 *__restrict__ node4, float4 *__restrict__ velacc,
+                            int *__restrict__ sorted, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    node4[i] = make_float4(x[i], y[i], z[i], mass[i]);
+    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+    velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    sorted[i] = 0;
+}
+
+// comp 0..3 of node4 for i < len
+__global__ void export_node_kernel(const float4 *__restrict__ node4, int comp, float *__restrict__ out, long long len) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    const float4 v = node4[i];
+    out[i] = comp == 0 ? v.x : comp == 1 ? v.y : comp == 2 ? v.z : v.w;
+}
+
+// which = 0 (vel) or 1 (acc); zeros beyond the bodies (the reference never writes there)
+__global__ void export_velacc_kernel(const float4 *__restrict__ velacc, int which, int comp, float *__restrict__ out,
+                                     int n, long long len) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    float r = 0.0f;
+    if (i < n) {
+        const float4 v = velacc[2 * (size_t)i + which];
+        r = comp == 0 ? v.x : comp == 1 ? v.y : v.z;
+    }
+    out[i] = r;
+}
+
+// logical int arrays that exist only for cells: zeros for the first `skip` entries
+__global__ void export_shifted_kernel(const int *__restrict__ src, long long skip, int *__restrict__ out, long long len) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    out[i] = i < skip ? 0 : src[i - skip];
+}
+
+// copyvertices.cl:14-17
+__global__ void copy_vertices_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ velacc,
+                                     float4 *__restrict__ pos, float4 *__restrict__ vel, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pos) {
+        const float4 p = node4[i];
+        pos[i] = make_float4(p.x, p.y, p.z, 1.0f);
+    }
+    if (vel) {
+        const float4 v = velacc[2 * (size_t)i];
+        vel[i] = make_float4(v.x, v.y, v.z, 1.0f);
+    }
+}
+
+}  // namespace bh

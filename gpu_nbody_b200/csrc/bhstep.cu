@@ -1,0 +1,580 @@
+// bhstep.cu -- host side of libbhstep.so: the C ABI declared in include/bhstep.h.
+//
+// Replaces the buffer / kernel / queue handling of
+// src/ch/fhnw/woipv/nbody/simulation/gpu/GPUBarnesHutNBodySimulation.java (GPUBH)
+// for the Barnes-Hut step.  No CPU fallback: without a CUDA device bh_create fails.
+#include "bh_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "bhstep.h"
+
+namespace {
+
+constexpr int kProfSteps = 64;  // steps per bh_step call that get per-stage events
+
+thread_local std::string g_createError;
+
+struct Sim {
+    int device = 0;
+    int n = 0, m = 0, nc = 0;  // bodies, NUMBER_OF_NODES, cell slots (m - n + 1)
+    float theta = 0.5f, thetaMacro = 0.25f, eps = 0.0025f, dt = 0.025f;
+    int vote = 16;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    // device state
+    float4 *node4 = nullptr, *velacc = nullptr, *octet = nullptr, *accSorted = nullptr;
+    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr;
+    float *partials = nullptr;
+    bh::Scalars *sc = nullptr;
+    bh::Scalars *hostSc = nullptr;  // pinned mirror
+    void *staging = nullptr;
+    size_t stagingBytes = 0;
+    // launch geometry
+    int bboxGrid = 1, buildGrid = 1, summGrid = 1, sortGrid = 1;
+    // options
+    bool profiling = false, counting = false;
+    int insertionOrder = 1;
+    bool haveSorted = false;
+    // profiling
+    cudaEvent_t ev[kProfSteps][BH_NUM_STAGES + 1] = {};
+    bool evCreated = false;
+    int evSteps = 0;
+    double stageMs[BH_NUM_STAGES] = {};
+    int64_t stageLaunches[BH_NUM_STAGES] = {};
+    int64_t stepsTimed = 0;
+    std::string lastError;
+};
+
+int fail(Sim *s, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (s) s->lastError = buf; else g_createError = buf;
+    return code;
+}
+
+#define BH_CUDA(s, call)                                                                               \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail((s), BH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline Sim *S(bh_sim *p) { return reinterpret_cast<Sim *>(p); }
+
+int ensureStaging(Sim *s, size_t bytes) {
+    if (bytes <= s->stagingBytes) return BH_OK;
+    if (s->staging) cudaFree(s->staging);
+    s->staging = nullptr;
+    s->stagingBytes = 0;
+    BH_CUDA(s, cudaMalloc(&s->staging, bytes));
+    s->stagingBytes = bytes;
+    return BH_OK;
+}
+
+int resetState(Sim *s) {
+    // GPUBH:155-179: everything zero except step = -1, maxDepth = 1
+    bh::Scalars init;
+    memset(&init, 0, sizeof init);
+    init.step = -1;
+    init.maxDepth = 1;
+    *s->hostSc = init;
+    BH_CUDA(s, cudaMemcpyAsync(s->sc, s->hostSc, sizeof init, cudaMemcpyHostToDevice, s->stream));
+    BH_CUDA(s, cudaMemsetAsync(s->child, 0, sizeof(int) * 8 * (size_t)s->nc, s->stream));
+    BH_CUDA(s, cudaMemsetAsync(s->start, 0, sizeof(int) * (size_t)s->nc, s->stream));
+    BH_CUDA(s, cudaMemsetAsync(s->count, 0, sizeof(int) * (size_t)s->nc, s->stream));
+    BH_CUDA(s, cudaMemsetAsync(s->node4 + s->n, 0, sizeof(float4) * (size_t)s->nc, s->stream));
+    s->haveSorted = false;
+    return BH_OK;
+}
+
+int launchStage(Sim *s, int stage) {
+    const int n = s->n, m = s->m;
+    switch (stage) {
+    case BH_STAGE_BBOX:
+        bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->node4, s->child, s->start, s->count,
+                                                                         s->partials, s->sc, n, m);
+        break;
+    case BH_STAGE_BUILD:
+        bh::build_kernel<<<s->buildGrid, bh::kBuildThreads, 0, s->stream>>>(
+            s->node4, s->child, s->start, s->count, (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
+        break;
+    case BH_STAGE_SUMMARIZE:
+        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->count,
+                                                                              s->sc, n, m);
+        break;
+    case BH_STAGE_SORT:
+        bh::sort_kernel<<<s->sortGrid, bh::kSortThreads, 0, s->stream>>>(s->child, s->count, s->start, s->sorted, s->sc, n, m);
+        s->haveSorted = true;
+        break;
+    case BH_STAGE_FORCE: {
+        const int grid = (n + bh::kForceThreads - 1) / bh::kForceThreads;
+        if (s->counting) {
+            BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
+            if (s->vote == 16)
+                bh::force_kernel<16, false, true><<<grid, bh::kForceThreads, 0, s->stream>>>(
+                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
+            else
+                bh::force_kernel<32, false, true><<<grid, bh::kForceThreads, 0, s->stream>>>(
+                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
+        } else {
+            if (s->vote == 16)
+                bh::force_kernel<16, false, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
+                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
+            else
+                bh::force_kernel<32, false, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
+                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
+        }
+        break;
+    }
+    case BH_STAGE_INTEGRATE:
+        bh::integrate_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, s->sc, n, s->dt);
+        break;
+    default:
+        return fail(s, BH_ERR_ARG, "unknown stage %d", stage);
+    }
+    BH_CUDA(s, cudaGetLastError());
+    s->stageLaunches[stage]++;
+    return BH_OK;
+}
+
+// sync, pull the scalars, report the device error buffer
+int finish(Sim *s) {
+    BH_CUDA(s, cudaMemcpyAsync(s->hostSc, s->sc, sizeof(bh::Scalars), cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (s->profiling && s->evSteps > 0) {
+        for (int i = 0; i < s->evSteps; ++i)
+            for (int st = 0; st < BH_NUM_STAGES; ++st) {
+                float ms = 0.0f;
+                if (cudaEventElapsedTime(&ms, s->ev[i][st], s->ev[i][st + 1]) == cudaSuccess) s->stageMs[st] += ms;
+            }
+        s->stepsTimed += s->evSteps;
+        s->evSteps = 0;
+    }
+    if (s->hostSc->error != 0) {
+        fail(s, s->hostSc->error, "device error buffer = %d (%s)", s->hostSc->error,
+             s->hostSc->error == 1 ? "cell pool exhausted or tree deeper than 64 levels" : "device-side wait exceeded its spin budget");
+        return s->hostSc->error;
+    }
+    return BH_OK;
+}
+
+int stepAsync(Sim *s, int nsteps) {
+    for (int i = 0; i < nsteps; ++i) {
+        const bool prof = s->profiling && s->evSteps < kProfSteps;
+        if (prof && !s->evCreated) {
+            for (auto &row : s->ev)
+                for (auto &e : row) BH_CUDA(s, cudaEventCreate(&e));
+            s->evCreated = true;
+        }
+        for (int st = 0; st < BH_NUM_STAGES; ++st) {
+            if (prof) BH_CUDA(s, cudaEventRecord(s->ev[s->evSteps][st], s->stream));
+            int rc = launchStage(s, st);
+            if (rc) return rc;
+        }
+        if (prof) {
+            BH_CUDA(s, cudaEventRecord(s->ev[s->evSteps][BH_NUM_STAGES], s->stream));
+            s->evSteps++;
+        }
+    }
+    return BH_OK;
+}
+
+int singleStage(Sim *s, int stage) {
+    const bool prof = s->profiling && s->evSteps < kProfSteps;
+    if (prof) {
+        // single stages are timed through one-off events folded into the same accumulators
+        cudaEvent_t a, b;
+        BH_CUDA(s, cudaEventCreate(&a));
+        BH_CUDA(s, cudaEventCreate(&b));
+        BH_CUDA(s, cudaEventRecord(a, s->stream));
+        int rc = launchStage(s, stage);
+        if (rc) return rc;
+        BH_CUDA(s, cudaEventRecord(b, s->stream));
+        rc = finish(s);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) s->stageMs[stage] += ms;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        return rc;
+    }
+    int rc = launchStage(s, stage);
+    if (rc) return rc;
+    return finish(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bh_abi_version(void) { return 1; }
+
+int32_t bh_number_of_nodes(int32_t nbodies) {
+    // GPUBH:219-227 with maxComputeUnits = 16 (GPUBH:126) and WARPSIZE = 16 (GPUBH:47)
+    int64_t nodes = (int64_t)nbodies * 2;
+    if (nodes < 1024 * 16) nodes = 1024 * 16;
+    while ((nodes & 15) != 0) ++nodes;
+    return nodes > INT32_MAX - 1 ? -1 : (int32_t)nodes;
+}
+
+const char *bh_last_error(bh_sim *sim) { return sim ? S(sim)->lastError.c_str() : g_createError.c_str(); }
+
+int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, int32_t vote_width, int32_t device) {
+    if (!out) return fail(nullptr, BH_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nbodies < 1) return fail(nullptr, BH_ERR_ARG, "nbodies must be >= 1");
+    if (vote_width != 16 && vote_width != 32) return fail(nullptr, BH_ERR_ARG, "vote_width must be 16 or 32");
+    const int32_t m = bh_number_of_nodes(nbodies);
+    // child rows are addressed as 8*(cell-N) in size_t; node indices must fit int32
+    if (m < 0) return fail(nullptr, BH_ERR_ARG, "nbodies too large for 32-bit node indices");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, BH_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, BH_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    Sim *s = new (std::nothrow) Sim();
+    if (!s) return fail(nullptr, BH_ERR_ALLOC, "out of host memory");
+    s->device = device;
+    s->n = nbodies;
+    s->m = m;
+    s->nc = m - nbodies + 1;
+    s->theta = theta;
+    s->thetaMacro = theta * theta;
+    s->eps = eps2;
+    s->dt = dt;
+    s->vote = vote_width;
+    auto bail = [&](int code, const char *what, cudaError_t e) {
+        fail(nullptr, code, "%s: %s", what, cudaGetErrorString(e));
+        bh_destroy(reinterpret_cast<bh_sim *>(s));
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaGetDeviceProperties", e);
+    s->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&s->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaStreamCreate", e);
+    s->stream = s->ownStream;
+    const size_t n = nbodies, nc = s->nc;
+#define BH_ALLOC(ptr, bytes) \
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes))) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMalloc " #ptr, e)
+    BH_ALLOC(s->node4, sizeof(float4) * ((size_t)m + 1));
+    BH_ALLOC(s->velacc, sizeof(float4) * 2 * n);
+    BH_ALLOC(s->octet, sizeof(float4) * 8 * nc);
+    BH_ALLOC(s->accSorted, sizeof(float4) * n);
+    BH_ALLOC(s->child, sizeof(int) * 8 * nc);
+    BH_ALLOC(s->start, sizeof(int) * nc);
+    BH_ALLOC(s->count, sizeof(int) * nc);
+    BH_ALLOC(s->sorted, sizeof(int) * n);
+    BH_ALLOC(s->sc, sizeof(bh::Scalars));
+#undef BH_ALLOC
+    if ((e = cudaMallocHost(reinterpret_cast<void **>(&s->hostSc), sizeof(bh::Scalars))) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMallocHost", e);
+    // launch geometry: streaming kernels a few CTAs per SM; the two kernels that wait on
+    // other threads (summarise, sort) exactly as many CTAs as are resident at once.
+    int perSM = 1;
+    s->bboxGrid = (int)std::min<size_t>((n + bh::kBboxThreads - 1) / bh::kBboxThreads, (size_t)s->numSMs * 4);
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&s->partials), sizeof(float) * 6 * s->bboxGrid)) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMalloc partials", e);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::build_kernel, bh::kBuildThreads, 0);
+    s->buildGrid = (int)std::min<size_t>((n + bh::kBuildThreads - 1) / bh::kBuildThreads, (size_t)s->numSMs * std::max(perSM, 1));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::summarize_kernel, bh::kSummThreads, 0);
+    s->summGrid = s->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::sort_kernel, bh::kSortThreads, 0);
+    s->sortGrid = s->numSMs * std::max(perSM, 1);
+    // tiny problems: do not launch more waiting threads than there can be cells
+    const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
+    s->summGrid = std::max(1, std::min(s->summGrid, cellBlocks));
+    s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
+    if ((e = cudaMemsetAsync(s->node4, 0, sizeof(float4) * ((size_t)m + 1), s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
+    cudaMemsetAsync(s->velacc, 0, sizeof(float4) * 2 * n, s->stream);
+    cudaMemsetAsync(s->sorted, 0, sizeof(int) * n, s->stream);
+    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * n, s->stream);
+    if (resetState(s) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+        g_createError = s->lastError.empty() ? "initial reset failed" : s->lastError;
+        bh_destroy(reinterpret_cast<bh_sim *>(s));
+        return BH_ERR_CUDA;
+    }
+    *out = reinterpret_cast<bh_sim *>(s);
+    return BH_OK;
+}
+
+void bh_destroy(bh_sim *sim) {
+    if (!sim) return;
+    Sim *s = S(sim);
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
+    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted);
+    cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
+    if (s->hostSc) cudaFreeHost(s->hostSc);
+    if (s->evCreated)
+        for (auto &row : s->ev)
+            for (auto &e : row) cudaEventDestroy(e);
+    if (s->ownStream) cudaStreamDestroy(s->ownStream);
+    delete s;
+}
+
+#define BH_ENTER(sim)                                          \
+    if (!(sim)) return BH_ERR_ARG;                             \
+    Sim *s = S(sim);                                           \
+    BH_CUDA(s, cudaSetDevice(s->device))
+
+int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
+    BH_ENTER(sim);
+    s->thetaMacro = theta_macro;
+    return BH_OK;
+}
+
+int bh_set_stream(bh_sim *sim, void *cuda_stream) {
+    BH_ENTER(sim);
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->ownStream;
+    return BH_OK;
+}
+
+int bh_set_profiling(bh_sim *sim, int32_t on) {
+    BH_ENTER(sim);
+    s->profiling = on != 0;
+    return BH_OK;
+}
+
+int bh_set_counting(bh_sim *sim, int32_t on) {
+    BH_ENTER(sim);
+    s->counting = on != 0;
+    return BH_OK;
+}
+
+int bh_set_insertion_order(bh_sim *sim, int32_t mode) {
+    BH_ENTER(sim);
+    if (mode != 0 && mode != 1) return fail(s, BH_ERR_ARG, "insertion order must be 0 or 1");
+    s->insertionOrder = mode;
+    return BH_OK;
+}
+
+static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind) {
+    for (int i = 0; i < 7; ++i)
+        if (!src[i]) return fail(s, BH_ERR_ARG, "NULL input array %d", i);
+    const size_t n = s->n;
+    const float *dev[7];
+    if (kind == cudaMemcpyHostToDevice) {
+        int rc = ensureStaging(s, sizeof(float) * 7 * n);
+        if (rc) return rc;
+        float *stg = static_cast<float *>(s->staging);
+        for (int i = 0; i < 7; ++i) {
+            BH_CUDA(s, cudaMemcpyAsync(stg + i * n, src[i], sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+            dev[i] = stg + i * n;
+        }
+    } else {
+        for (int i = 0; i < 7; ++i) dev[i] = src[i];
+    }
+    int rc = resetState(s);
+    if (rc) return rc;
+    bh::pack_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], s->node4,
+                                                              s->velacc, s->sorted, s->n);
+    BH_CUDA(s, cudaGetLastError());
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    return BH_OK;
+}
+
+int bh_upload(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+              const float *vz, const float *mass) {
+    BH_ENTER(sim);
+    const float *src[7] = {x, y, z, vx, vy, vz, mass};
+    return uploadImpl(s, src, cudaMemcpyHostToDevice);
+}
+
+int bh_upload_device(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+                     const float *vz, const float *mass) {
+    BH_ENTER(sim);
+    const float *src[7] = {x, y, z, vx, vy, vz, mass};
+    return uploadImpl(s, src, cudaMemcpyDeviceToDevice);
+}
+
+int bh_bounding_box(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_BBOX); }
+int bh_build_tree(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_BUILD); }
+int bh_summarize(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_SUMMARIZE); }
+int bh_sort(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_SORT); }
+int bh_calculate_force(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_FORCE); }
+int bh_integrate(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_INTEGRATE); }
+
+int bh_stage_async(bh_sim *sim, int32_t stage) { BH_ENTER(sim); return launchStage(s, stage); }
+
+int bh_step_async(bh_sim *sim, int32_t nsteps) {
+    BH_ENTER(sim);
+    if (nsteps < 0) return fail(s, BH_ERR_ARG, "nsteps < 0");
+    return stepAsync(s, nsteps);
+}
+
+int bh_check(bh_sim *sim) { BH_ENTER(sim); return finish(s); }
+
+int bh_step(bh_sim *sim, int32_t nsteps) {
+    BH_ENTER(sim);
+    if (nsteps < 0) return fail(s, BH_ERR_ARG, "nsteps < 0");
+    // chunks of kProfSteps so that per-stage events never run out
+    while (nsteps > 0) {
+        const int chunk = s->profiling ? std::min<int>(nsteps, kProfSteps) : nsteps;
+        int rc = stepAsync(s, chunk);
+        if (rc) return rc;
+        if (s->profiling || chunk == nsteps) {
+            rc = finish(s);
+            if (rc) return rc;
+        }
+        nsteps -= chunk;
+    }
+    return BH_OK;
+}
+
+int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
+    BH_ENTER(sim);
+    if (first < 0 || count < 0 || (int64_t)first + count > s->n || (first % s->vote) != 0)
+        return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
+    if (count == 0) return BH_OK;
+    const int grid = (count + bh::kForceThreads - 1) / bh::kForceThreads;
+    if (s->vote == 16)
+        bh::force_kernel<16, true, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
+            s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, count, s->thetaMacro, s->eps, s->dt);
+    else
+        bh::force_kernel<32, true, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
+            s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, count, s->thetaMacro, s->eps, s->dt);
+    BH_CUDA(s, cudaGetLastError());
+    s->stageLaunches[BH_STAGE_FORCE]++;
+    return BH_OK;
+}
+
+int bh_apply_acceleration(bh_sim *sim) {
+    BH_ENTER(sim);
+    bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->accSorted, s->sorted, s->velacc, s->sc, s->n, s->dt);
+    BH_CUDA(s, cudaGetLastError());
+    s->stageLaunches[BH_STAGE_FORCE]++;
+    return BH_OK;
+}
+
+void *bh_acc_sorted_device_ptr(bh_sim *sim) { return sim ? S(sim)->accSorted : nullptr; }
+
+int64_t bh_buffer_length(bh_sim *sim, int32_t which) {
+    if (!sim) return BH_ERR_ARG;
+    Sim *s = S(sim);
+    const int64_t m1 = (int64_t)s->m + 1;
+    switch (which) {
+    case BH_STEP: case BH_BLOCK_COUNT: case BH_RADIUS: case BH_MAX_DEPTH: case BH_BOTTOM: case BH_ERROR: return 1;
+    case BH_CHILD: return 8 * m1;
+    default: return (which >= 0 && which < BH_NUM_BUFFERS) ? m1 : (int64_t)BH_ERR_ARG;
+    }
+}
+
+int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
+    BH_ENTER(sim);
+    const int64_t len = bh_buffer_length(sim, which);
+    if (len < 0) return fail(s, BH_ERR_ARG, "unknown buffer %d", which);
+    if (!dst || count < 0 || count > len) return fail(s, BH_ERR_ARG, "bad destination/count for buffer %d", which);
+    if (count == 0) return BH_OK;
+    if (len == 1) {
+        BH_CUDA(s, cudaMemcpyAsync(s->hostSc, s->sc, sizeof(bh::Scalars), cudaMemcpyDeviceToHost, s->stream));
+        BH_CUDA(s, cudaStreamSynchronize(s->stream));
+        const bh::Scalars &h = *s->hostSc;
+        switch (which) {
+        case BH_STEP: *static_cast<int32_t *>(dst) = h.step; break;
+        case BH_BLOCK_COUNT: *static_cast<int32_t *>(dst) = h.blockCount; break;
+        case BH_RADIUS: *static_cast<float *>(dst) = h.radius; break;
+        case BH_MAX_DEPTH: *static_cast<int32_t *>(dst) = h.maxDepth; break;
+        case BH_BOTTOM: *static_cast<int32_t *>(dst) = h.bottom; break;
+        default: *static_cast<int32_t *>(dst) = h.error; break;
+        }
+        return BH_OK;
+    }
+    int rc = ensureStaging(s, 4 * (size_t)count);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    switch (which) {
+    case BH_POS_X: case BH_POS_Y: case BH_POS_Z:
+        bh::export_node_kernel<<<grid, 256, 0, s->stream>>>(s->node4, which - BH_POS_X, static_cast<float *>(s->staging), count);
+        break;
+    case BH_MASS:
+        bh::export_node_kernel<<<grid, 256, 0, s->stream>>>(s->node4, 3, static_cast<float *>(s->staging), count);
+        break;
+    case BH_VEL_X: case BH_VEL_Y: case BH_VEL_Z:
+        bh::export_velacc_kernel<<<grid, 256, 0, s->stream>>>(s->velacc, 0, which - BH_VEL_X, static_cast<float *>(s->staging), s->n, count);
+        break;
+    case BH_ACC_X: case BH_ACC_Y: case BH_ACC_Z:
+        bh::export_velacc_kernel<<<grid, 256, 0, s->stream>>>(s->velacc, 1, which - BH_ACC_X, static_cast<float *>(s->staging), s->n, count);
+        break;
+    case BH_BODY_COUNT:
+        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->count, s->n, static_cast<int *>(s->staging), count);
+        break;
+    case BH_START:
+        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->start, s->n, static_cast<int *>(s->staging), count);
+        break;
+    case BH_CHILD:
+        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->child, 8 * (long long)s->n, static_cast<int *>(s->staging), count);
+        break;
+    case BH_SORTED: {
+        const int64_t head = std::min<int64_t>(count, s->n);
+        BH_CUDA(s, cudaMemcpyAsync(s->staging, s->sorted, 4 * (size_t)head, cudaMemcpyDeviceToDevice, s->stream));
+        if (count > head) BH_CUDA(s, cudaMemsetAsync(static_cast<int *>(s->staging) + head, 0, 4 * (size_t)(count - head), s->stream));
+        break;
+    }
+    default:
+        return fail(s, BH_ERR_ARG, "unknown buffer %d", which);
+    }
+    BH_CUDA(s, cudaGetLastError());
+    BH_CUDA(s, cudaMemcpyAsync(dst, s->staging, 4 * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    return BH_OK;
+}
+
+int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4) {
+    BH_ENTER(sim);
+    if (!pos4 && !vel4) return BH_OK;
+    const size_t bytes = sizeof(float4) * (size_t)s->n;
+    int rc = ensureStaging(s, 2 * bytes);
+    if (rc) return rc;
+    float4 *dp = static_cast<float4 *>(s->staging), *dv = dp + s->n;
+    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, pos4 ? dp : nullptr, vel4 ? dv : nullptr, s->n);
+    BH_CUDA(s, cudaGetLastError());
+    if (pos4) BH_CUDA(s, cudaMemcpyAsync(pos4, dp, bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (vel4) BH_CUDA(s, cudaMemcpyAsync(vel4, dv, bytes, cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    return BH_OK;
+}
+
+int bh_stats(bh_sim *sim, bh_stats_t *out) {
+    BH_ENTER(sim);
+    if (!out) return fail(s, BH_ERR_ARG, "out is NULL");
+    BH_CUDA(s, cudaMemcpyAsync(s->hostSc, s->sc, sizeof(bh::Scalars), cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    memset(out, 0, sizeof *out);
+    out->nbodies = s->n;
+    out->number_of_nodes = s->m;
+    out->cells_used = s->m - s->hostSc->bottom + 1;
+    out->max_depth = s->hostSc->maxDepth;
+    out->step = s->hostSc->step;
+    out->error = s->hostSc->error;
+    out->steps_timed = s->stepsTimed;
+    for (int i = 0; i < BH_NUM_STAGES; ++i) {
+        out->stage_ms[i] = s->stageMs[i];
+        out->stage_launches[i] = s->stageLaunches[i];
+    }
+    out->interactions = (int64_t)s->hostSc->interactions;
+    out->opens = (int64_t)s->hostSc->opens;
+    return BH_OK;
+}
+
+int bh_reset_stats(bh_sim *sim) {
+    BH_ENTER(sim);
+    for (int i = 0; i < BH_NUM_STAGES; ++i) {
+        s->stageMs[i] = 0.0;
+        s->stageLaunches[i] = 0;
+    }
+    s->stepsTimed = 0;
+    return BH_OK;
+}
+
+int32_t bh_number_of_bodies(bh_sim *sim) { return sim ? S(sim)->n : BH_ERR_ARG; }
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+/*
+ * bhstep.h -- C ABI of libbhstep.so, the B200 (sm_100a) Barnes-Hut step.
+ *
+ * This is the drop-in boundary for the hot path of bneukom/gpu-nbody: every
+ * entry point replaces a JOCL/OOCL call sequence of
+ *   src/ch/fhnw/woipv/nbody/simulation/gpu/GPUBarnesHutNBodySimulation.java
+ * (cited as GPUBH below; kernel sources under kernels/nbody/).  Plain C types
+ * only; no torch, no CUDA types (a stream travels as void*).  All functions
+ * return 0 on success, a negative bh_status on CUDA/argument failure (text via
+ * bh_last_error) and a positive value when the device `error` buffer is set
+ * (1 = cell pool exhausted or tree deeper than 64 levels, exactly the two
+ * conditions of buildtree.cl:112-119 and calculateforce.cl:69-73;
+ * 2 = a device-side wait exceeded its spin budget).
+ *
+ * Threading: a bh_sim is thread-compatible, not thread-safe (the reference is
+ * driven from one JOGL animator thread, NBodyVisualizer.java:460-470).  Every
+ * call selects the simulation's device first, so JVM callers may hop threads.
+ *
+ * There is no CPU fallback: bh_create fails with BH_ERR_NO_DEVICE when no
+ * CUDA device is present.
+ */
+#ifndef BHSTEP_H
+#define BHSTEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bh_sim bh_sim; /* opaque; one per simulation and device */
+
+enum bh_status {
+    BH_OK = 0,
+    BH_ERR_CUDA = -1,      /* a CUDA runtime call failed                    */
+    BH_ERR_ARG = -2,       /* bad argument                                  */
+    BH_ERR_NO_DEVICE = -3, /* no CUDA device (GPUBH:120 IllegalStateException) */
+    BH_ERR_ALLOC = -4
+};
+
+/* Logical buffers in the reference's kernel-argument order (GPUBH:198-205). */
+enum bh_buffer {
+    BH_POS_X = 0, BH_POS_Y, BH_POS_Z,     /* float[M+1]  bodies 0..N-1, cells N..M (root M) */
+    BH_VEL_X, BH_VEL_Y, BH_VEL_Z,         /* float[M+1]  */
+    BH_ACC_X, BH_ACC_Y, BH_ACC_Z,         /* float[M+1]  */
+    BH_STEP,                              /* int[1]      */
+    BH_BLOCK_COUNT,                       /* int[1]      */
+    BH_BODY_COUNT,                        /* int[M+1]    */
+    BH_RADIUS,                            /* float[1]    */
+    BH_MAX_DEPTH,                         /* int[1]      */
+    BH_BOTTOM,                            /* int[1]      */
+    BH_MASS,                              /* float[M+1]  */
+    BH_CHILD,                             /* int[8(M+1)] */
+    BH_START,                             /* int[M+1]    */
+    BH_SORTED,                            /* int[M+1]    */
+    BH_ERROR,                             /* int[1]      */
+    BH_NUM_BUFFERS
+};
+
+enum bh_stage { BH_STAGE_BBOX = 0, BH_STAGE_BUILD, BH_STAGE_SUMMARIZE, BH_STAGE_SORT, BH_STAGE_FORCE,
+                BH_STAGE_INTEGRATE, BH_NUM_STAGES };
+
+typedef struct bh_stats_t {
+    int32_t nbodies;          /* N */
+    int32_t number_of_nodes;  /* M  (GPUBH:219-227) */
+    int32_t cells_used;       /* M - bottom + 1 after the last build */
+    int32_t max_depth;        /* running maximum, as in the reference */
+    int32_t step;             /* value of the `step` buffer */
+    int32_t error;            /* value of the `error` buffer */
+    int64_t steps_timed;      /* stage executions accumulated in stage_ms (profiling on) */
+    double stage_ms[BH_NUM_STAGES];      /* summed CUDA-event time per stage */
+    int64_t stage_launches[BH_NUM_STAGES]; /* kernel launches per stage since reset */
+    int64_t interactions;     /* (body,node) force evaluations of the last counted force call */
+    int64_t opens;            /* (body,cell) opening tests that pushed, same call */
+} bh_stats_t;
+
+/* GPUBH.init():111-151 -- context, node-pool sizing (219-227), buffer creation (153-181).
+ * theta is the opening angle (the reference's THETA macro is theta^2,
+ * calculateforce.cl:15-16); eps2 is EPSILON (added to r^2); dt is TIMESTEP;
+ * vote_width is the reference's WARPSIZE/WORKGROUP_SIZE (16 = parity; 32 = one
+ * vote per hardware warp, not reference-exact). */
+int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, int32_t vote_width, int32_t device);
+void bh_destroy(bh_sim *sim);
+const char *bh_last_error(bh_sim *sim); /* sim may be NULL: error of the last failed bh_create */
+
+/* Override theta^2 directly (e.g. the shipped THETA (1.5f), calculateforce.cl:16). */
+int bh_set_theta_macro(bh_sim *sim, float theta_macro);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the simulation's own. */
+int bh_set_stream(bh_sim *sim, void *cuda_stream);
+/* 1 = record CUDA events around every stage (bh_stats.stage_ms); 0 = off (default). */
+int bh_set_profiling(bh_sim *sim, int32_t on);
+/* 1 = count interactions/opens in the next force calls (slower kernel variant); 0 = off. */
+int bh_set_counting(bh_sim *sim, int32_t on);
+/* Order in which build_tree inserts bodies: 0 = index order, 1 = previous step's
+ * sorted (DFS / Morton-like) order.  The resulting tree is identical. */
+int bh_set_insertion_order(bh_sim *sim, int32_t mode);
+
+/* createBuffer(CL_MEM_COPY_HOST_PTR, ...) for the seven generator outputs (GPUBH:155-170):
+ * caller-owned host SoA arrays of length nbodies are copied; all other buffers are
+ * reset to their initial values (step=-1, maxDepth=1, rest 0). */
+int bh_upload(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+              const float *vz, const float *mass);
+/* Same with device pointers (inputs already resident in HBM). */
+int bh_upload_device(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+                     const float *vz, const float *mass);
+
+/* The per-stage kernel contract, one call per executeSimulationKernel (GPUBH:258-263,273-275).
+ * Each enqueues on the simulation's stream and waits for it, like finish() at GPUBH:275. */
+int bh_bounding_box(bh_sim *sim);    /* kernels/nbody/boundingbox.cl:21     */
+int bh_build_tree(bh_sim *sim);      /* kernels/nbody/buildtree.cl:13       */
+int bh_summarize(bh_sim *sim);       /* kernels/nbody/summarizetree.cl:16   */
+int bh_sort(bh_sim *sim);            /* kernels/nbody/sort.cl:13            */
+int bh_calculate_force(bh_sim *sim); /* kernels/nbody/calculateforce.cl:26  */
+int bh_integrate(bh_sim *sim);       /* kernels/nbody/integrate.cl:18       */
+
+/* GPUBH.step():249-271, nsteps times: the six stages in order, no host sync
+ * between them, one sync and one look at the error buffer at the end. */
+int bh_step(bh_sim *sim, int32_t nsteps);
+/* Same without the final sync (caller synchronises its stream, then bh_check). */
+int bh_step_async(bh_sim *sim, int32_t nsteps);
+int bh_check(bh_sim *sim); /* sync + error buffer */
+
+/* Multi-GPU slice contract (no counterpart in the single-device reference).
+ * bh_calculate_force_slice walks the tree for sorted slots [first, first+count)
+ * (first a multiple of vote_width) and stores float4 {ax,ay,az,0} per slot into
+ * the sorted-order acceleration buffer; after the caller has all-gathered that
+ * buffer across ranks, bh_apply_acceleration performs the velocity correction
+ * and acc store of calculateforce.cl:174-185 for all N bodies.  Both async. */
+int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count);
+int bh_apply_acceleration(bh_sim *sim);
+void *bh_acc_sorted_device_ptr(bh_sim *sim); /* float4[N] in device memory */
+/* Async single stages for callers that sequence their own stream. */
+int bh_stage_async(bh_sim *sim, int32_t stage /* enum bh_stage */);
+
+/* queue.readBuffer(mem) + mem.getData() (GPUBH:277-278,294-295,306-312): copies the first
+ * `count` elements of logical buffer `which` to host memory, in the reference's
+ * index conventions whatever the internal layout. */
+int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count);
+int64_t bh_buffer_length(bh_sim *sim, int32_t which);
+
+/* kernels/nbody/copyvertices.cl:8-17 with host destinations: pos4[i] = {x,y,z,1},
+ * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
+int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
+
+int bh_stats(bh_sim *sim, bh_stats_t *out);
+int bh_reset_stats(bh_sim *sim);
+int32_t bh_number_of_bodies(bh_sim *sim);          /* getNumberOfBodies(), GPUBH:377-379 */
+int32_t bh_number_of_nodes(int32_t nbodies);       /* calculateNumberOfNodes, GPUBH:219-227 */
+int32_t bh_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHSTEP_H */

@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs (run with ``pytest -m gpu`` on the B200 box)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from gpu_nbody_b200 import BhError, GPUBarnesHutNBodySimulation, Mode, universe as U
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bundled(name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n = d["x"].size
+    z = np.zeros(n, dtype=np.float32)
+    return [d["x"], d["y"], d["z"], z, z.copy(), z.copy(), np.full(n, d["mass"][0], dtype=np.float32)]
+
+
+def gen(generator, n):
+    return U.generate_arrays(generator, n)
+
+
+# ---- the reference's hand-written test universes (universe/test/*.java) ----------------
+@pytest.mark.parametrize("generator,n", [(U.TwoBodyUniverse(), 2), (U.EightBodyUniverse(), 8), (U.BigTreeUniverse(), 4)])
+def test_reference_test_universes(generator, n):
+    sim, orc = parity.make_pair(gen(generator, n))
+    parity.check_full_step(sim, orc)
+    sim.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 16, 17, 100, 1000, 4096])
+def test_small_and_ragged_sizes(n):
+    """N below one vote group, not a multiple of 16/32, around one CTA."""
+    sim, orc = parity.make_pair(gen(U.PlummerUniverseGenerator(seed=n), n))
+    parity.check_full_step(sim, orc)
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["sphericaluniverse1", "montecarlouniverse1"])
+def test_bundled_universe_three_steps(name):
+    """BASELINE config 1: the bundled 32768-body universes, theta = 0.5."""
+    sim, orc = parity.make_pair(bundled(name))
+    for _ in range(3):
+        parity.sync_oracle_from_gpu(sim, orc)
+        parity.check_full_step(sim, orc)
+    assert sim.scalar("step") == 2
+    sim.close()
+
+
+def test_bundled_universe_shipped_theta():
+    """The THETA (1.5f) the reference ships with (calculateforce.cl:16)."""
+    sim, orc = parity.make_pair(bundled("sphericaluniverse1"), theta_macro=1.5)
+    parity.check_full_step(sim, orc)
+    sim.close()
+
+
+@pytest.mark.parametrize("generator,n", [
+    (U.PlummerUniverseGenerator(42), 262144),
+    (U.RandomCubicUniverseGenerator(6.0, 44), 131072),
+    (U.TwoDiskGalaxiesGenerator(45, 46), 131072),
+    (U.SphericalUniverseGenerator(47), 50000),
+])
+def test_distributions(generator, n):
+    sim, orc = parity.make_pair(gen(generator, n))
+    for _ in range(2):
+        parity.sync_oracle_from_gpu(sim, orc)
+        parity.check_full_step(sim, orc)
+    sim.close()
+
+
+@pytest.mark.parametrize("theta", [0.3, 0.8])
+def test_theta_sweep(theta):
+    sim, orc = parity.make_pair(gen(U.TwoDiskGalaxiesGenerator(45, 46), 65536), theta=theta)
+    parity.check_full_step(sim, orc)
+    sim.close()
+
+
+def test_vote_width_32_mode():
+    """The non-reference 32-wide vote: still the oracle's semantics at vote_width = 32."""
+    sim, orc = parity.make_pair(gen(U.PlummerUniverseGenerator(7), 32768), vote_width=32)
+    parity.check_full_step(sim, orc)
+    sim.close()
+
+
+def test_insertion_order_does_not_change_the_tree():
+    arrays = gen(U.PlummerUniverseGenerator(11), 65536)
+    results = []
+    for mode in (0, 1):
+        sim, orc = parity.make_pair(arrays)
+        sim.setInsertionOrder(mode)
+        sim.step(2)           # second step inserts in the first step's sorted order when mode = 1
+        parity.sync_oracle_from_gpu(sim, orc)
+        parity.check_full_step(sim, orc)
+        results.append([sim.readBuffer(k, 65536) for k in ("posX", "velX", "sorted")])
+        sim.close()
+    for a, b in zip(*results):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_step_equals_stage_sequence_and_is_deterministic():
+    """bh_step(k) == k x the six stage calls (GPUBH:258-263); run to run bit-identical."""
+    arrays = gen(U.PlummerUniverseGenerator(5), 20000)
+    outs = []
+    for use_step in (True, False, True):
+        sim, _ = parity.make_pair(arrays, counting=False)
+        if use_step:
+            sim.step(3)
+        else:
+            for _ in range(3):
+                sim.boundingBox(); sim.buildTree(); sim.summarizeTree(); sim.sort(); sim.calculateForce(); sim.integrate()
+        outs.append([sim.readBuffer(k, 20000) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "sorted")])
+        assert sim.scalar("step") == 2
+        sim.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_energy_drift_100_steps_matches_oracle():
+    """north_star: matched total-energy drift over 100 steps at the same theta and dt."""
+    import oracle
+    n = 4096
+    arrays = gen(U.PlummerUniverseGenerator(3), n)
+    sim, orc = parity.make_pair(arrays, counting=False)
+    e0 = sum(orc.energy())
+    sim.step(100)
+    assert orc.step(100) == 0
+    g = [sim.readBuffer(k, n) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "mass")]
+    eg = sum(oracle.energy(*g))
+    eo = sum(orc.energy())
+    drift_g, drift_o = (eg - e0) / abs(e0), (eo - e0) / abs(e0)
+    # both integrate the same Hamiltonian with the same scheme; trajectories diverge
+    # chaotically at the 1e-7 level, the energy error does not
+    assert abs(drift_o) < 5e-3 and abs(drift_g) < 5e-3, (drift_g, drift_o)
+    assert abs(drift_g - drift_o) < 5e-4, (drift_g, drift_o)
+    sim.close()
+
+
+def test_coincident_bodies_report_error_1():
+    """buildtree.cl:112-119: identical positions exhaust the pool -> error = 1, no hang."""
+    n = 64
+    a = gen(U.PlummerUniverseGenerator(1), n)
+    for k in range(3):
+        a[k][10] = a[k][3]
+    sim, _ = parity.make_pair(a, counting=False)
+    with pytest.raises(BhError) as ei:
+        sim.step(1)
+    assert ei.value.code == 1
+    assert sim.scalar("error") == 1
+    sim.close()
+
+
+def test_copy_vertices_and_read_conventions():
+    n = 1000
+    a = gen(U.PlummerUniverseGenerator(2), n)
+    sim = GPUBarnesHutNBodySimulation(Mode.GL_INTEROP, n, U.ArrayUniverseGenerator(*a))
+    sim.init(None)
+    sim.initGLBuffers(None, -1, -1)
+    assert sim.getNumberOfBodies() == n
+    assert sim.scalar("step") == -1 and sim.scalar("maxDepth") == 1  # GPUBH:165,170
+    sim.step()
+    pos4, vel4 = sim.copyVertices()
+    assert np.array_equal(pos4[:, 0], sim.readBuffer("posX", n)) and np.all(pos4[:, 3] == 1.0)
+    assert np.array_equal(vel4[:, 2], sim.readBuffer("velZ", n)) and np.all(vel4[:, 3] == 1.0)
+    m = sim.numberOfNodes
+    assert sim.readBuffer("child").size == 8 * (m + 1) and sim.readBuffer("velX").size == m + 1
+    assert not sim.readBuffer("velX")[n:].any() and not sim.readBuffer("sorted")[n:].any()
+    sim.close()
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 2 size (Plummer 2^20): size-independent properties instead of the oracle."""
+    n = 1 << 20
+    a = gen(U.PlummerUniverseGenerator(42), n)
+    sim, _ = parity.make_pair(a, counting=True)
+    sim.step(1)
+    st = sim.stats()
+    srt = sim.readBuffer("sorted", n)
+    assert np.array_equal(np.sort(srt), np.arange(n, dtype=np.int32))
+    m = sim.numberOfNodes
+    assert sim.readBuffer("bodyCount")[m] == n
+    mass = sim.readBuffer("mass")
+    assert abs(float(mass[m]) - float(a[6].astype(np.float64).sum())) < 1e-3
+    # root COM = mass-weighted mean of the bodies (pre-integrate positions)
+    com = [float((a[k].astype(np.float64) * a[6]).sum() / a[6].astype(np.float64).sum()) for k in range(3)]
+    # positions moved by one integrate since summarise; COM of the root is from before
+    root = [float(sim.readBuffer(k)[m]) for k in ("posX", "posY", "posZ")]
+    assert np.allclose(root, com, atol=1e-4)
+    assert 0.4 < st["cells_used"] / n < 0.6 and 10 <= st["max_depth"] <= 40
+    assert 2000 < st["interactions"] / n < 4000
+    # momentum conservation of the tree force: |sum m a| small against sum m |a|
+    acc = np.stack([sim.readBuffer(k, n) for k in ("accX", "accY", "accZ")], axis=1).astype(np.float64)
+    mm = a[6].astype(np.float64)[:, None]
+    assert np.linalg.norm((mm * acc).sum(axis=0)) < 1e-2 * (mm * np.linalg.norm(acc, axis=1)[:, None]).sum()
+    # spot-check 512 bodies against the direct softened sum
+    import oracle
+    ax, ay, az = oracle.direct_acc(a[0], a[1], a[2], a[6], 0, 512)
+    d = np.stack([ax, ay, az], axis=1)
+    err = np.linalg.norm(acc[:512] - d, axis=1) / np.linalg.norm(d, axis=1)
+    assert np.median(err) < 5e-3
+    sim.close()
