@@ -61,7 +61,7 @@ def check_bounding_box(sim, orc):
         assert_bits_equal(sim.readBuffer(name)[m], orc.buf[name][m], "root " + name)
     assert_bits_equal(sim.scalar("radius"), orc.radius[0], "radius")
     assert sim.scalar("bottom") == m == orc.bottom[0]
-    assert sim.scalar("step") == orc.step[0]
+    assert sim.scalar("step") == orc.buf["step"][0]
     assert sim.scalar("blockCount") == 0
     assert sim.readBuffer("mass")[m] == -1.0 and sim.readBuffer("start")[m] == 0
     assert (sim.readBuffer("child")[8 * m:] == -1).all()
