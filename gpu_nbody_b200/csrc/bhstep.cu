@@ -17,6 +17,7 @@
 namespace {
 
 constexpr int kProfSteps = 64;  // steps per bh_step call that get per-stage events
+constexpr size_t kAccPad = 2048; // slack of the sorted-order acceleration buffer: equal, 32-aligned slices for up to 64 ranks
 
 thread_local std::string g_createError;
 
@@ -268,7 +269,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->node4, sizeof(float4) * ((size_t)m + 1));
     BH_ALLOC(s->velacc, sizeof(float4) * 2 * n);
     BH_ALLOC(s->octet, sizeof(float4) * 8 * nc);
-    BH_ALLOC(s->accSorted, sizeof(float4) * n);
+    BH_ALLOC(s->accSorted, sizeof(float4) * (n + kAccPad));
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
@@ -294,7 +295,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     if ((e = cudaMemsetAsync(s->node4, 0, sizeof(float4) * ((size_t)m + 1), s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
     cudaMemsetAsync(s->velacc, 0, sizeof(float4) * 2 * n, s->stream);
     cudaMemsetAsync(s->sorted, 0, sizeof(int) * n, s->stream);
-    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * n, s->stream);
+    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * (n + kAccPad), s->stream);
     if (resetState(s) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
         g_createError = s->lastError.empty() ? "initial reset failed" : s->lastError;
         bh_destroy(reinterpret_cast<bh_sim *>(s));
@@ -576,5 +577,34 @@ int bh_reset_stats(bh_sim *sim) {
 }
 
 int32_t bh_number_of_bodies(bh_sim *sim) { return sim ? S(sim)->n : BH_ERR_ARG; }
+
+int bh_measure_fp32_peak(int32_t device, double *tflops) {
+    if (!tflops) return BH_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, BH_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BH_ERR_CUDA;
+    float *out = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&out), 4) != cudaSuccess) return BH_ERR_ALLOC;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(a);
+        bh::fp32_peak_kernel<<<grid, 256>>>(out, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    *tflops = best;
+    return best > 0.0 ? BH_OK : BH_ERR_CUDA;
+}
 
 }  // extern "C"

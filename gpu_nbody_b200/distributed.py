@@ -1,0 +1,105 @@
+"""Multi-GPU Barnes-Hut step: one process per GPU, torch.distributed for the plumbing.
+
+The reference is single-device (one CLDevice, GPUBarnesHutNBodySimulation.java:120);
+this is the one natural shard of its step (DESIGN.md "Multi-GPU"):
+
+  every rank   bounding box -> build tree -> summarise -> sort   (replicated, identical trees)
+  rank p       force walk for the sorted slots [first_p, first_p + count_p)
+  all ranks    all-gather of the sorted-order acceleration slices (NCCL over NVLink)
+  every rank   velocity correction + integrate for all bodies      (replicated, 68 B/body of HBM)
+
+Slices are equal-sized multiples of 32 sorted slots, so vote groups are exactly
+those of the single-GPU run and the all-gather is in place.  What crosses NVLink
+is 16 B per body per step (float4 acceleration); positions never travel because
+the integrate is replicated and bit-deterministic.
+
+`engine` is anything with the stage methods below (the CUDA simulation in
+production; the CPU oracle in the world_size-2 gloo tests), `gather` performs
+the all-gather on the engine's sorted-order acceleration buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from .simulation import GPUBarnesHutNBodySimulation
+
+SLICE_ALIGN = 32  # a hardware warp = two 16-body vote groups
+
+
+def slice_bounds(nbodies: int, world_size: int, align: int = SLICE_ALIGN):
+    """Equal slices of `chunk` sorted slots (chunk a multiple of `align`); the last
+    non-empty slice is cut at nbodies.  Returns (chunk, [(first, count)] per rank)."""
+    chunk = -(-nbodies // world_size)
+    chunk = -(-chunk // align) * align
+    bounds = []
+    for r in range(world_size):
+        first = min(r * chunk, nbodies)
+        bounds.append((first, max(0, min(chunk, nbodies - first))))
+    return chunk, bounds
+
+
+class CudaSliceEngine:
+    """Adapter from GPUBarnesHutNBodySimulation to the slice contract of include/bhstep.h."""
+
+    def __init__(self, sim: GPUBarnesHutNBodySimulation):
+        import torch
+        self.sim = sim
+        self.lib = sim._lib
+        self.h = sim.handle
+        self.nbodies = sim.nbodies
+        self.device = torch.device("cuda", sim.device)
+        ptr = self.lib.bh_acc_sorted_device_ptr(self.h)
+        cap = sim.nbodies + 2048
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (cap, 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+        self._keep = _Buf()
+        self.acc_sorted = torch.as_tensor(self._keep, device=self.device)
+        assert self.acc_sorted.data_ptr() == int(ptr)
+        # run on torch's current stream so that NCCL ops and kernels are ordered
+        sim.setStream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _rc(self, rc):
+        self.sim._check(rc)
+
+    def tree_stages(self):
+        for st in range(4):  # bbox, build, summarise, sort
+            self._rc(self.lib.bh_stage_async(self.h, st))
+
+    def force_slice(self, first, count):
+        self._rc(self.lib.bh_calculate_force_slice(self.h, first, count))
+
+    def apply_and_integrate(self):
+        self._rc(self.lib.bh_apply_acceleration(self.h))
+        self._rc(self.lib.bh_stage_async(self.h, 5))
+
+    def check(self):
+        self._rc(self.lib.bh_check(self.h))
+
+
+class DistributedBarnesHutSimulation:
+    """step() for world_size ranks; with world_size == 1 it degenerates to slice = everything."""
+
+    def __init__(self, engine, rank: int, world_size: int, group=None):
+        self.engine, self.rank, self.world_size, self.group = engine, rank, world_size, group
+        self.chunk, self.bounds = slice_bounds(engine.nbodies, world_size)
+        if self.chunk * world_size > engine.acc_sorted.shape[0]:
+            raise ValueError("acceleration buffer too small for %d ranks" % world_size)
+
+    def step_async(self, nsteps: int = 1):
+        import torch.distributed as dist
+        first, count = self.bounds[self.rank]
+        full = self.engine.acc_sorted[: self.chunk * self.world_size]
+        mine = full[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+        for _ in range(nsteps):
+            self.engine.tree_stages()
+            self.engine.force_slice(first, count)
+            if self.world_size > 1:
+                dist.all_gather_into_tensor(full, mine, group=self.group)
+            self.engine.apply_and_integrate()
+
+    def step(self, nsteps: int = 1):
+        self.step_async(nsteps)
+        self.engine.check()

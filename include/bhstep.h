@@ -128,7 +128,7 @@ int bh_check(bh_sim *sim); /* sync + error buffer */
  * and acc store of calculateforce.cl:174-185 for all N bodies.  Both async. */
 int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count);
 int bh_apply_acceleration(bh_sim *sim);
-void *bh_acc_sorted_device_ptr(bh_sim *sim); /* float4[N] in device memory */
+void *bh_acc_sorted_device_ptr(bh_sim *sim); /* float4[N + 2048] in device memory (slack for equal, aligned slices) */
 /* Async single stages for callers that sequence their own stream. */
 int bh_stage_async(bh_sim *sim, int32_t stage /* enum bh_stage */);
 
@@ -147,6 +147,9 @@ int bh_reset_stats(bh_sim *sim);
 int32_t bh_number_of_bodies(bh_sim *sim);          /* getNumberOfBodies(), GPUBH:377-379 */
 int32_t bh_number_of_nodes(int32_t nbodies);       /* calculateNumberOfNodes, GPUBH:219-227 */
 int32_t bh_abi_version(void);
+/* Measurement utility (no reference counterpart): sustained FP32 FMA rate of `device`
+ * in TFLOP/s, the roofline denominator bench.py uses for the force kernel. */
+int bh_measure_fp32_peak(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }
