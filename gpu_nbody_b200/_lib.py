@@ -69,9 +69,11 @@ def load():
         "bh_last_error": (C.c_char_p, [p]),
         "bh_set_theta_macro": (C.c_int, [p, f32]),
         "bh_set_stream": (C.c_int, [p, p]),
+        "bh_use_private_stream": (C.c_int, [p]),
         "bh_set_profiling": (C.c_int, [p, i32]),
         "bh_set_counting": (C.c_int, [p, i32]),
         "bh_set_insertion_order": (C.c_int, [p, i32]),
+        "bh_set_force_variant": (C.c_int, [p, i32]),
         "bh_upload": (C.c_int, [p] + [p] * 7),
         "bh_upload_device": (C.c_int, [p] + [p] * 7),
         "bh_bounding_box": (C.c_int, [p]),

@@ -20,6 +20,7 @@
 //   octet  float4[8*NC]  copy of the node4 records of a cell's (compacted)
 //                        children, written by summarise: the force walk reads a
 //                        cell's children as one 128-byte line.
+//   meta   int[NC]       number of children | (bitmask of children that are cells) << 8
 //   start, count int[NC] `start` and `bodyCount` of the reference; count doubles
 //                        as the "summarised" flag (-1 = not yet).
 //   sorted int[N]        bodies in tree (DFS) order.
@@ -258,8 +259,8 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
 constexpr int kSummThreads = 256;
 
 __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
-                                                                 float4 *__restrict__ octet, int *count, Scalars *sc,
-                                                                 int n, int m) {
+                                                                 float4 *__restrict__ octet, int *__restrict__ meta, int *count,
+                                                                 Scalars *sc, int n, int m) {
     if (sc->error != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->bottom = m;  // buildtree.cl:117
         return;
@@ -317,6 +318,10 @@ __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restr
         }
         reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
         reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
+        int cellMask = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cellMask |= (out[k] >= n) ? (1 << k) : 0;
+        meta[cell - n] = used | (cellMask << 8);  // force walk: child count + which children are cells
         const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
         __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
         st_release(count + (cell - n), bodies);  // summarizetree.cl:160,170-172: data first, flag last
@@ -470,6 +475,170 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(const float4 *__re
             velacc[2 * (size_t)body] = v;
         }
         velacc[2 * (size_t)body + 1] = make_float4(ax, ay, az, 0.0f);  // :183-185
+    }
+}
+
+
+// ---- 5b. force, packed ---------------------------------------------------------
+// Same contract as force_kernel, rebuilt around Blackwell's packed fp32 pipe
+// (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot).  The walk is
+// issue-bound, so every lane carries TWO consecutive sorted bodies and a warp
+// carries 64 bodies = 64/VOTE vote groups (lanes 8g..8g+7 are group g for
+// VOTE = 16).  A stack entry is {cell, lane mask of the groups that still need
+// it, depth}; a group that accepted a cell is simply absent from the mask of its
+// children.  Per child: one 16-byte octet load, 7 packed fp32 ops for both
+// distances, one ballot (cells only), two MUFU.RSQ, 6 packed ops for the force.
+constexpr int kForce2Threads = 256;
+constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
+
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    // r^2 >= EPSILON > 0 is never subnormal: the bare MUFU.RSQ (2 ulp, calculateforce.cl:146 allows rsqrt's 2 ulp)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// calculateforce.cl:146-151 for the lane's two bodies; mw = child mass, or 0 for a lane whose group does not use the child
+__device__ __forceinline__ void force_accumulate(float2 dx, float2 dy, float2 dz, float2 r2, float mw, float2 &ax, float2 &ay,
+                                                 float2 &az) {
+    const float2 rinv = make_float2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
+    const float2 f = __fmul2_rn(__fmul2_rn(__fmul2_rn(make_float2(mw, mw), rinv), rinv), rinv);
+    ax = __ffma2_rn(dx, f, ax);
+    ay = __ffma2_rn(dy, f, ay);
+    az = __ffma2_rn(dz, f, az);
+}
+
+template <int VOTE, bool SLICE, bool COUNT>
+__global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
+                                                                 const int *__restrict__ child, const int *__restrict__ meta,
+                                                                 const int *__restrict__ sorted, float4 *__restrict__ velacc,
+                                                                 float4 *__restrict__ accSorted, Scalars *sc, int n, int m,
+                                                                 int first, int cnt, float thetaMacro, float eps, float dt) {
+    __shared__ float dq[kMaxDepth];
+    __shared__ int2 stackA[kForce2Threads / 32][kStackCap];  // {cell, lane mask}
+    __shared__ int stackD[kForce2Threads / 32][kStackCap];   // depth
+    if (sc->error != 0) return;
+    const int maxDepth = sc->maxDepth;
+    if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
+        return;
+    }
+    if (threadIdx.x == 0) {  // calculateforce.cl:52-67
+        const float radius = sc->radius;
+        float v = __fmul_rn(radius, radius);
+        if (thetaMacro > 0.0f) v = __fdiv_rn(v, thetaMacro);
+        for (int i = 0; i < maxDepth; ++i) {
+            dq[i] = __fadd_rn(v, eps);
+            v = __fmul_rn(0.25f, v);
+        }
+    }
+    __syncthreads();
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int end = first + cnt;
+    const int base = first + (blockIdx.x * (kForce2Threads / 32) + warp) * 64;
+    if (base >= end) return;
+    // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
+    const int k0 = base + 2 * lane;
+    const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
+    constexpr int kLanesPerGroup = VOTE / 2;
+    const int gfirst = lane & ~(kLanesPerGroup - 1);  // first lane of my group
+    unsigned gm = ((kLanesPerGroup == 32) ? kFull : ((1u << kLanesPerGroup) - 1u)) << gfirst;
+    asm volatile("" : "+r"(gm));  // keep the group mask in a register (ptxas would rematerialise it per vote)
+    // a slot past the end borrows the position of the group's first body: its vote then equals that body's
+    const int kg = base + 2 * gfirst;
+    const int s0 = (nact > 0) ? k0 : min(kg, end - 1), s1 = (nact > 1) ? k0 + 1 : s0;
+    const int b0 = sorted[s0], b1 = sorted[s1];
+    const float4 p0 = node4[b0], p1 = node4[b1];
+    const float2 npx = make_float2(-p0.x, -p1.x), npy = make_float2(-p0.y, -p1.y), npz = make_float2(-p0.z, -p1.z);
+    const float2 eps2 = make_float2(eps, eps);
+    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+    unsigned long long nInter = 0, nOpen = 0;
+    int2 *stA = stackA[warp];
+    int *stD = stackD[warp];
+    // groups with at least one existing body take part in the walk
+    const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
+    unsigned startMask = 0;
+#pragma unroll
+    for (int g = 0; g < 32 / kLanesPerGroup; ++g) {
+        const unsigned m1 = ((kLanesPerGroup == 32) ? kFull : ((1u << kLanesPerGroup) - 1u)) << (g * kLanesPerGroup);
+        if (lanesActive & m1) startMask |= m1;
+    }
+    int sp = 0;
+    stA[0] = make_int2(m, (int)startMask);
+    stD[0] = 0;
+    sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int2 e = stA[sp];
+        const int d = stD[sp];
+        __syncwarp();  // every lane has read the entry before any lane may overwrite the slot
+        const unsigned lmask = (unsigned)e.y;
+        const bool mine = (lmask >> lane) & 1u;
+        const float thr = dq[d];
+        const size_t ci = (size_t)(e.x - n) * 8;
+        const int mt = __ldg(meta + (e.x - n));
+        const int nch = mt & 15;
+        const unsigned cmask = (unsigned)mt >> 8;
+        const float4 *orow = octet + ci;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j >= nch) break;
+            const float4 c = __ldg(orow + j);
+            const float2 dx = __fadd2_rn(make_float2(c.x, c.x), npx);  // c - p, exactly
+            const float2 dy = __fadd2_rn(make_float2(c.y, c.y), npy);
+            const float2 dz = __fadd2_rn(make_float2(c.z, c.z), npz);
+            const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2);  // :138-143
+            if ((cmask >> j) & 1u) {  // a cell: the group votes (calculateforce.cl:145)
+                const unsigned far = __ballot_sync(kFull, r2.x >= thr && r2.y >= thr);
+                const bool groupFar = (~far & gm) == 0u;
+                const unsigned open = __ballot_sync(kFull, mine && !groupFar);
+                if (open) {  // :154-163
+                    const int ch = __ldg(child + ci + j);
+                    stA[sp] = make_int2(ch, (int)open);
+                    stD[sp] = d + 1;
+                    ++sp;
+                }
+                if (COUNT && mine && !groupFar) nOpen += nact;
+                if (lmask & ~open) {  // at least one group uses the cell as a point mass
+                    force_accumulate(dx, dy, dz, r2, (mine && groupFar) ? c.w : 0.0f, ax, ay, az);
+                    if (COUNT && mine && groupFar) nInter += nact;
+                }
+            } else {  // a body: always used (:145 child < NBODIES)
+                force_accumulate(dx, dy, dz, r2, mine ? c.w : 0.0f, ax, ay, az);
+                if (COUNT && mine) nInter += nact;
+            }
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            nInter += __shfl_xor_sync(kFull, nInter, o);
+            nOpen += __shfl_xor_sync(kFull, nOpen, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sc->interactions, nInter);
+            atomicAdd(&sc->opens, nOpen);
+        }
+    }
+    const bool corr = sc->step > 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (t >= nact) break;
+        const int body = t ? b1 : b0;
+        const float fx = t ? ax.y : ax.x, fy = t ? ay.y : ay.x, fz = t ? az.y : az.x;
+        if (SLICE) {
+            accSorted[k0 + t] = make_float4(fx, fy, fz, 0.0f);
+        } else {
+            if (corr) {  // calculateforce.cl:174-179
+                float4 v = velacc[2 * (size_t)body];
+                const float4 a0 = velacc[2 * (size_t)body + 1];
+                v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(fx, a0.x), dt), 0.5f));
+                v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(fy, a0.y), dt), 0.5f));
+                v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(fz, a0.z), dt), 0.5f));
+                velacc[2 * (size_t)body] = v;
+            }
+            velacc[2 * (size_t)body + 1] = make_float4(fx, fy, fz, 0.0f);  // :183-185
+        }
     }
 }
 

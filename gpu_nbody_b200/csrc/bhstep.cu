@@ -30,7 +30,7 @@ struct Sim {
     cudaStream_t stream = nullptr, ownStream = nullptr;
     // device state
     float4 *node4 = nullptr, *velacc = nullptr, *octet = nullptr, *accSorted = nullptr;
-    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr;
+    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr;
     float *partials = nullptr;
     bh::Scalars *sc = nullptr;
     bh::Scalars *hostSc = nullptr;  // pinned mirror
@@ -41,6 +41,7 @@ struct Sim {
     // options
     bool profiling = false, counting = false;
     int insertionOrder = 1;
+    int forceVariant = 2;
     bool haveSorted = false;
     // profiling
     cudaEvent_t ev[kProfSteps][BH_NUM_STAGES + 1] = {};
@@ -97,6 +98,33 @@ int resetState(Sim *s) {
     return BH_OK;
 }
 
+// force walk for sorted slots [first, first+cnt): fused velocity correction (slice = false) or
+// sorted-order acceleration output (slice = true)
+void launchForce(Sim *s, int first, int cnt, bool slice, bool counting) {
+#define BH_FORCE_ARGS1 s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
+#define BH_FORCE_ARGS2 s->node4, s->octet, s->child, s->meta, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
+#define BH_FORCE_DISPATCH(KERNEL, THREADS, BODIES, ARGS)                                                     \
+    do {                                                                                                     \
+        const int grid = (cnt + (BODIES) - 1) / (BODIES);                                                     \
+        if (s->vote == 16) {                                                                                 \
+            if (slice) KERNEL<16, true, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                       \
+            else if (counting) KERNEL<16, false, true><<<grid, THREADS, 0, s->stream>>>(ARGS);               \
+            else KERNEL<16, false, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                            \
+        } else {                                                                                             \
+            if (slice) KERNEL<32, true, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                       \
+            else if (counting) KERNEL<32, false, true><<<grid, THREADS, 0, s->stream>>>(ARGS);               \
+            else KERNEL<32, false, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                            \
+        }                                                                                                    \
+    } while (0)
+    if (s->forceVariant == 1)
+        BH_FORCE_DISPATCH(bh::force_kernel, bh::kForceThreads, bh::kForceThreads, BH_FORCE_ARGS1);
+    else
+        BH_FORCE_DISPATCH(bh::force2_kernel, bh::kForce2Threads, bh::kForce2Bodies, BH_FORCE_ARGS2);
+#undef BH_FORCE_DISPATCH
+#undef BH_FORCE_ARGS1
+#undef BH_FORCE_ARGS2
+}
+
 int launchStage(Sim *s, int stage) {
     const int n = s->n, m = s->m;
     switch (stage) {
@@ -109,7 +137,7 @@ int launchStage(Sim *s, int stage) {
             s->node4, s->child, s->start, s->count, (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
         break;
     case BH_STAGE_SUMMARIZE:
-        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->count,
+        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->meta, s->count,
                                                                               s->sc, n, m);
         break;
     case BH_STAGE_SORT:
@@ -117,23 +145,8 @@ int launchStage(Sim *s, int stage) {
         s->haveSorted = true;
         break;
     case BH_STAGE_FORCE: {
-        const int grid = (n + bh::kForceThreads - 1) / bh::kForceThreads;
-        if (s->counting) {
-            BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
-            if (s->vote == 16)
-                bh::force_kernel<16, false, true><<<grid, bh::kForceThreads, 0, s->stream>>>(
-                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
-            else
-                bh::force_kernel<32, false, true><<<grid, bh::kForceThreads, 0, s->stream>>>(
-                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
-        } else {
-            if (s->vote == 16)
-                bh::force_kernel<16, false, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
-                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
-            else
-                bh::force_kernel<32, false, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
-                    s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, n, m, 0, n, s->thetaMacro, s->eps, s->dt);
-        }
+        if (s->counting) BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
+        launchForce(s, 0, n, false, s->counting);
         break;
     }
     case BH_STAGE_INTEGRATE:
@@ -273,6 +286,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
+    BH_ALLOC(s->meta, sizeof(int) * nc);
     BH_ALLOC(s->sorted, sizeof(int) * n);
     BH_ALLOC(s->sc, sizeof(bh::Scalars));
 #undef BH_ALLOC
@@ -311,7 +325,7 @@ void bh_destroy(bh_sim *sim) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
-    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted);
+    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta);
     cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
@@ -335,7 +349,14 @@ int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
 int bh_set_stream(bh_sim *sim, void *cuda_stream) {
     BH_ENTER(sim);
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
-    s->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->ownStream;
+    s->stream = reinterpret_cast<cudaStream_t>(cuda_stream);  // NULL = CUDA's default stream, as everywhere in CUDA
+    return BH_OK;
+}
+
+int bh_use_private_stream(bh_sim *sim) {
+    BH_ENTER(sim);
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->stream = s->ownStream;
     return BH_OK;
 }
 
@@ -348,6 +369,13 @@ int bh_set_profiling(bh_sim *sim, int32_t on) {
 int bh_set_counting(bh_sim *sim, int32_t on) {
     BH_ENTER(sim);
     s->counting = on != 0;
+    return BH_OK;
+}
+
+int bh_set_force_variant(bh_sim *sim, int32_t variant) {
+    BH_ENTER(sim);
+    if (variant != 1 && variant != 2) return fail(s, BH_ERR_ARG, "force variant must be 1 or 2");
+    s->forceVariant = variant;
     return BH_OK;
 }
 
@@ -436,13 +464,7 @@ int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
     if (first < 0 || count < 0 || (int64_t)first + count > s->n || (first % s->vote) != 0)
         return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
     if (count == 0) return BH_OK;
-    const int grid = (count + bh::kForceThreads - 1) / bh::kForceThreads;
-    if (s->vote == 16)
-        bh::force_kernel<16, true, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
-            s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, count, s->thetaMacro, s->eps, s->dt);
-    else
-        bh::force_kernel<32, true, false><<<grid, bh::kForceThreads, 0, s->stream>>>(
-            s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, count, s->thetaMacro, s->eps, s->dt);
+    launchForce(s, first, count, true, false);
     BH_CUDA(s, cudaGetLastError());
     s->stageLaunches[BH_STAGE_FORCE]++;
     return BH_OK;

@@ -85,8 +85,11 @@ const char *bh_last_error(bh_sim *sim); /* sim may be NULL: error of the last fa
 
 /* Override theta^2 directly (e.g. the shipped THETA (1.5f), calculateforce.cl:16). */
 int bh_set_theta_macro(bh_sim *sim, float theta_macro);
-/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the simulation's own. */
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = CUDA's default
+ * stream).  A new simulation runs on a private non-blocking stream; bh_use_private_stream
+ * returns to it. */
 int bh_set_stream(bh_sim *sim, void *cuda_stream);
+int bh_use_private_stream(bh_sim *sim);
 /* 1 = record CUDA events around every stage (bh_stats.stage_ms); 0 = off (default). */
 int bh_set_profiling(bh_sim *sim, int32_t on);
 /* 1 = count interactions/opens in the next force calls (slower kernel variant); 0 = off. */
@@ -94,6 +97,9 @@ int bh_set_counting(bh_sim *sim, int32_t on);
 /* Order in which build_tree inserts bodies: 0 = index order, 1 = previous step's
  * sorted (DFS / Morton-like) order.  The resulting tree is identical. */
 int bh_set_insertion_order(bh_sim *sim, int32_t mode);
+/* Force-walk kernel: 2 (default) = two bodies per lane on the packed fp32x2 pipe,
+ * 1 = one body per lane (scalar fp32).  Same interactions, same votes. */
+int bh_set_force_variant(bh_sim *sim, int32_t variant);
 
 /* createBuffer(CL_MEM_COPY_HOST_PTR, ...) for the seven generator outputs (GPUBH:155-170):
  * caller-owned host SoA arrays of length nbodies are copied; all other buffers are
