@@ -491,6 +491,8 @@ __global__ void __launch_bounds__(kForceThreads) force_kernel(const float4 *__re
 constexpr int kForce2Threads = 256;
 constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float rsqrt_fast(float x) {
     // r^2 >= EPSILON > 0 is never subnormal: the bare MUFU.RSQ (2 ulp, calculateforce.cl:146 allows rsqrt's 2 ulp)
     float r;
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     __shared__ float dq[kMaxDepth];
     __shared__ int2 stackA[kForce2Threads / 32][kStackCap];  // {cell, lane mask}
     __shared__ int stackD[kForce2Threads / 32][kStackCap];   // depth
+    __shared__ float4 stage[kForce2Threads / 32][12];        // the popped cell's row: 8 children, 8 indices, meta
     if (sc->error != 0) return;
     const int maxDepth = sc->maxDepth;
     if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
@@ -537,7 +540,6 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int end = first + cnt;
     const int base = first + (blockIdx.x * (kForce2Threads / 32) + warp) * 64;
-    if (base >= end) return;
     // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
     const int k0 = base + 2 * lane;
     const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
@@ -567,48 +569,78 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     int sp = 0;
     stA[0] = make_int2(m, (int)startMask);
     stD[0] = 0;
-    sp = 1;
+    sp = startMask != 0u ? 1 : 0;
+    // Row fetch: one LDG.128 per pop brings the cell's whole record -- 8 child {x,y,z,m} (lanes 0-7), 8 child
+    // indices (lanes 8-9) and the meta word (lane 10) -- into a per-warp shared-memory row; the children are
+    // then consumed with broadcast LDS.128.  (Per-child global loads miss L1 once per 32-byte sector, i.e. on
+    // every second child, and each miss stalls the warp for an L2 round trip.)
+    const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
+                           : lane < 10 ? reinterpret_cast<const char *>(child) + 16 * (lane - 8)
+                                       : reinterpret_cast<const char *>(meta);
+    const int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+    float4 *row = stage[warp];
+    const int *rowInt = reinterpret_cast<const int *>(row);
     while (sp > 0) {
         --sp;
         const int2 e = stA[sp];
         const int d = stD[sp];
-        __syncwarp();  // every lane has read the entry before any lane may overwrite the slot
+        __syncwarp();  // every lane has read the entry (and is done with the previous row)
+        const int rel = e.x - n;
+        if (lane < 11) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(laneBase + (size_t)rel * laneStride) & ~uintptr_t(15);
+            row[lane] = __ldg(reinterpret_cast<const float4 *>(addr));
+        }
         const unsigned lmask = (unsigned)e.y;
         const bool mine = (lmask >> lane) & 1u;
+        const unsigned gmMine = mine ? gm : 0u;  // my group's lanes if my group still needs this cell
+        const unsigned notMine = mine ? 0u : kFull;
         const float thr = dq[d];
-        const size_t ci = (size_t)(e.x - n) * 8;
-        const int mt = __ldg(meta + (e.x - n));
+        __syncwarp();
+        // REDUX puts the (warp-uniform) word into a uniform register: ptxas then knows that the
+        // branches on it are uniform and emits no divergence guards around the votes
+        const int mt = __reduce_or_sync(kFull, rowInt[40 + (rel & 3)]);
         const int nch = mt & 15;
         const unsigned cmask = (unsigned)mt >> 8;
-        const float4 *orow = octet + ci;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j >= nch) break;
-            const float4 c = __ldg(orow + j);
-            const float2 dx = __fadd2_rn(make_float2(c.x, c.x), npx);  // c - p, exactly
-            const float2 dy = __fadd2_rn(make_float2(c.y, c.y), npy);
-            const float2 dz = __fadd2_rn(make_float2(c.z, c.z), npz);
-            const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2);  // :138-143
-            if ((cmask >> j) & 1u) {  // a cell: the group votes (calculateforce.cl:145)
-                const unsigned far = __ballot_sync(kFull, r2.x >= thr && r2.y >= thr);
-                const bool groupFar = (~far & gm) == 0u;
-                const unsigned open = __ballot_sync(kFull, mine && !groupFar);
-                if (open) {  // :154-163
-                    const int ch = __ldg(child + ci + j);
-                    stA[sp] = make_int2(ch, (int)open);
-                    stD[sp] = d + 1;
-                    ++sp;
-                }
-                if (COUNT && mine && !groupFar) nOpen += nact;
-                if (lmask & ~open) {  // at least one group uses the cell as a point mass
-                    force_accumulate(dx, dy, dz, r2, (mine && groupFar) ? c.w : 0.0f, ax, ay, az);
-                    if (COUNT && mine && groupFar) nInter += nact;
-                }
-            } else {  // a body: always used (:145 child < NBODIES)
-                force_accumulate(dx, dy, dz, r2, mine ? c.w : 0.0f, ax, ay, az);
-                if (COUNT && mine) nInter += nact;
-            }
+#define BH_CHILD(j)                                                                                                  \
+    {                                                                                                                \
+        const float4 c = row[j];                                                                                     \
+        const float2 dx = __fadd2_rn(make_float2(c.x, c.x), npx); /* c - p, exactly */                               \
+        const float2 dy = __fadd2_rn(make_float2(c.y, c.y), npy);                                                    \
+        const float2 dz = __fadd2_rn(make_float2(c.z, c.z), npz);                                                    \
+        const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2); /* :138-143 */ \
+        if ((cmask >> (j)) & 1u) { /* a cell: the group votes (calculateforce.cl:145) */                            \
+            const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr));                               \
+            const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                       \
+            if (open) { /* :154-163 */                                                                               \
+                const int ch = rowInt[32 + (j)];                                                                     \
+                stA[sp] = make_int2(ch, (int)open);                                                                  \
+                stD[sp] = d + 1;                                                                                     \
+                ++sp;                                                                                                \
+                if (lane < 11) prefetch_l1(laneBase + (size_t)(ch - n) * laneStride);                                \
+            }                                                                                                        \
+            const bool use = ((near & gm) | notMine) == 0u;                                                          \
+            if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                       \
+            if (lmask & ~open) { /* at least one group uses the cell as a point mass */                             \
+                force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);                                      \
+                if (COUNT && use) nInter += nact;                                                                    \
+            }                                                                                                        \
+        } else { /* a body: always used (:145 child < NBODIES) */                                                   \
+            force_accumulate(dx, dy, dz, r2, mine ? c.w : 0.0f, ax, ay, az);                                         \
+            if (COUNT && mine) nInter += nact;                                                                       \
+        }                                                                                                            \
+    }
+        switch (nch) {  // children are compacted: evaluate slots nch-1 .. 0, one jump instead of a test per child
+        case 8: BH_CHILD(7)
+        case 7: BH_CHILD(6)
+        case 6: BH_CHILD(5)
+        case 5: BH_CHILD(4)
+        case 4: BH_CHILD(3)
+        case 3: BH_CHILD(2)
+        case 2: BH_CHILD(1)
+        case 1: BH_CHILD(0)
+        default: break;
         }
+#undef BH_CHILD
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {

@@ -286,7 +286,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
-    BH_ALLOC(s->meta, sizeof(int) * nc);
+    BH_ALLOC(s->meta, sizeof(int) * (nc + 4));  // +4: the force walk reads the aligned int4 around an entry
     BH_ALLOC(s->sorted, sizeof(int) * n);
     BH_ALLOC(s->sc, sizeof(bh::Scalars));
 #undef BH_ALLOC
