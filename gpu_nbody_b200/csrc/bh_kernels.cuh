@@ -5,7 +5,7 @@
 //   build_kernel      <- kernels/nbody/buildtree.cl
 //   summarize_kernel  <- kernels/nbody/summarizetree.cl
 //   sort_kernel       <- kernels/nbody/sort.cl
-//   force_kernel      <- kernels/nbody/calculateforce.cl
+//   force2_kernel     <- kernels/nbody/calculateforce.cl
 //   integrate_kernel  <- kernels/nbody/integrate.cl
 // They reproduce the reference's *results* (see DESIGN.md for the parity classes),
 // not its code: the data layout, work decomposition and synchronisation are
@@ -17,10 +17,9 @@
 //                        mass = -1; summarise overwrites it with {COM, mass}.
 //   velacc float4[2N]    {vx,vy,vz,0},{ax,ay,az,0} per body: one 32-byte sector.
 //   child  int[8*NC]     child[(cell-N)*8 + k]; -1 empty, -2 locked, <N body, >=N cell
-//   octet  float4[8*NC]  copy of the node4 records of a cell's (compacted)
-//                        children, written by summarise: the force walk reads a
-//                        cell's children as one 128-byte line.
-//   meta   int[NC]       number of children | (bitmask of children that are cells) << 8
+//   octet  float4[8*NC]  the force walk's record of a cell: copies of its children's node4
+//   oidx   int[8*NC]     records, child cells first, then child bodies (128-byte line), the
+//   meta   int[NC]       child cells' indices minus N, and #cells | #bodies << 4.  Written by summarise.
 //   start, count int[NC] `start` and `bodyCount` of the reference; count doubles
 //                        as the "summarised" flag (-1 = not yet).
 //   sorted int[N]        bodies in tree (DFS) order.
@@ -259,8 +258,8 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
 constexpr int kSummThreads = 256;
 
 __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
-                                                                 float4 *__restrict__ octet, int *__restrict__ meta, int *count,
-                                                                 Scalars *sc, int n, int m) {
+                                                                 float4 *__restrict__ octet, int *__restrict__ oidx,
+                                                                 int *__restrict__ meta, int *count, Scalars *sc, int n, int m) {
     if (sc->error != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->bottom = m;  // buildtree.cl:117
         return;
@@ -286,7 +285,13 @@ __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restr
         float cm = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
         int bodies = used;  // summarizetree.cl:118
         bool ok = true;
+        // walk record of this cell for the force kernel: child cells first, then child bodies
         float4 *orow = octet + (size_t)(cell - n) * 8;
+        int *irow = oidx + (size_t)(cell - n) * 8;
+        int ncell = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ncell += (out[k] >= n) ? 1 : 0;
+        int cpos = 0, bpos = ncell;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int ch = out[k];
@@ -303,10 +308,12 @@ __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restr
                 if (!ok) break;
                 bodies += cnt - 1;  // summarizetree.cl:98-105
                 c = __ldcg(node4 + ch);
+                irow[cpos] = ch - n;
+                orow[cpos++] = c;
             } else {
                 c = node4[ch];
+                orow[bpos++] = c;
             }
-            orow[k] = c;
             cm = __fadd_rn(cm, c.w);  // summarizetree.cl:107-110
             cx = fmaf(c.x, c.w, cx);
             cy = fmaf(c.y, c.w, cy);
@@ -318,10 +325,7 @@ __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restr
         }
         reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
         reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
-        int cellMask = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cellMask |= (out[k] >= n) ? (1 << k) : 0;
-        meta[cell - n] = used | (cellMask << 8);  // force walk: child count + which children are cells
+        meta[cell - n] = ncell | ((used - ncell) << 4);  // force walk: #child cells, #child bodies
         const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
         __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
         st_release(count + (cell - n), bodies);  // summarizetree.cl:160,170-172: data first, flag last
@@ -362,132 +366,27 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restric
     }
 }
 
+constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 children, 7 stay while the 8th is walked
+
 // ---- 5. force -------------------------------------------------------------------
 // calculateforce.cl: a vote group of VOTE consecutive sorted bodies walks the tree
 // together; a cell is used as a point mass only if *all* bodies of the group
-// are far enough (work_group_all, :145), bodies are always used.  Here one
-// hardware warp carries 32/VOTE groups through ONE shared walk: each stack entry
-// records which groups still need the cell, a group that accepted a cell simply
-// is not in the mask of that cell's children.  The set of (group, node)
-// interactions is exactly the reference's; the order in which a body sums them
-// differs (children of a popped cell are consumed before its opened children
-// are descended), which moves the fp32 sum by rounding only.
-constexpr int kForceThreads = 256;
-constexpr int kStackCap = 7 * kMaxDepth + 8;
-
-template <int VOTE, bool SLICE, bool COUNT>
-__global__ void __launch_bounds__(kForceThreads) force_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
-                                                               const int *__restrict__ child, const int *__restrict__ sorted,
-                                                               float4 *__restrict__ velacc, float4 *__restrict__ accSorted,
-                                                               Scalars *sc, int n, int m, int first, int cnt,
-                                                               float thetaMacro, float eps, float dt) {
-    __shared__ float dq[kMaxDepth];
-    __shared__ int2 stack[kForceThreads / 32][kStackCap];
-    if (sc->error != 0) return;
-    const int maxDepth = sc->maxDepth;
-    if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
-        if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
-        return;
-    }
-    if (threadIdx.x == 0) {  // calculateforce.cl:52-67
-        const float radius = sc->radius;
-        float v = __fmul_rn(radius, radius);
-        if (thetaMacro > 0.0f) v = __fdiv_rn(v, thetaMacro);
-        for (int i = 0; i < maxDepth; ++i) {
-            dq[i] = __fadd_rn(v, eps);
-            v = __fmul_rn(0.25f, v);
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int end = first + cnt;
-    const int base = first + (blockIdx.x * (kForceThreads / 32) + warp) * 32;
-    if (base >= end) return;
-    const int k = base + lane;
-    const bool active = k < end;
-    const int body = sorted[active ? k : base];
-    const float4 p = node4[body];
-    constexpr unsigned kFull = 0xffffffffu;
-    const int h = (VOTE == 16) ? (lane >> 4) : 0;  // which vote group of the warp this lane is in
-    const unsigned act = __ballot_sync(kFull, active);
-    int groups = (VOTE == 16) ? (((act & 0xffffu) ? 1 : 0) | ((act >> 16) ? 2 : 0)) : 1;
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    unsigned long long nInter = 0, nOpen = 0;
-    int2 *stk = stack[warp];
-    int sp = 0;
-    stk[sp++] = make_int2(m, groups);  // depth 0 in bits 2.., group mask in bits 0..1
-    while (sp > 0) {
-        const int2 e = stk[--sp];
-        __syncwarp();  // every lane has read the entry before any lane may overwrite the slot
-        const int mask = e.y & 3, d = e.y >> 2;
-        const float thr = dq[d];
-        const size_t ci = (size_t)(e.x - n) * 8;
-        const int4 lo = __ldg(reinterpret_cast<const int4 *>(child + ci));
-        const int4 hi = __ldg(reinterpret_cast<const int4 *>(child + ci) + 1);
-        const int chs[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int ch = chs[j];
-            if (ch < 0) break;  // children are compacted (summarizetree.cl:77-81)
-            const float4 c = __ldg(octet + ci + j);
-            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-            const float r2 = __fadd_rn(fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx))), eps);  // :138-143
-            int use = mask;
-            if (ch >= n) {
-                const unsigned far = __ballot_sync(kFull, r2 >= thr || !active);
-                const int all = (VOTE == 16) ? ((((far & 0xffffu) == 0xffffu) ? 1 : 0) | (((far >> 16) == 0xffffu) ? 2 : 0))
-                                             : ((far == kFull) ? 1 : 0);
-                use = mask & all;
-                const int open = mask & ~all;
-                if (open) stk[sp++] = make_int2(ch, open | ((d + 1) << 2));  // :154-163
-                if (COUNT && active && ((open >> h) & 1)) ++nOpen;
-            }
-            if ((use >> h) & 1) {  // :146-151
-                const float rinv = rsqrtf(r2);
-                const float f = __fmul_rn(__fmul_rn(__fmul_rn(c.w, rinv), rinv), rinv);
-                ax = fmaf(dx, f, ax);
-                ay = fmaf(dy, f, ay);
-                az = fmaf(dz, f, az);
-                if (COUNT && active) ++nInter;
-            }
-        }
-    }
-    if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) {
-            nInter += __shfl_xor_sync(kFull, nInter, o);
-            nOpen += __shfl_xor_sync(kFull, nOpen, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&sc->interactions, nInter);
-            atomicAdd(&sc->opens, nOpen);
-        }
-    }
-    if (!active) return;
-    if (SLICE) {
-        accSorted[k] = make_float4(ax, ay, az, 0.0f);
-    } else {
-        float4 v = velacc[2 * (size_t)body];
-        if (sc->step > 0) {  // calculateforce.cl:174-179
-            const float4 a0 = velacc[2 * (size_t)body + 1];
-            v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(ax, a0.x), dt), 0.5f));
-            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(ay, a0.y), dt), 0.5f));
-            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(az, a0.z), dt), 0.5f));
-            velacc[2 * (size_t)body] = v;
-        }
-        velacc[2 * (size_t)body + 1] = make_float4(ax, ay, az, 0.0f);  // :183-185
-    }
-}
-
-
-// ---- 5b. force, packed ---------------------------------------------------------
-// Same contract as force_kernel, rebuilt around Blackwell's packed fp32 pipe
+// are far enough (work_group_all, :145), bodies are always used.  The set of
+// (group, node) interactions is exactly the reference's; the order in which a
+// body sums them differs (all children of a popped cell are consumed before its
+// opened children are descended), which moves the fp32 sum by rounding only.
+// The kernel is built around Blackwell's packed fp32 pipe
 // (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot).  The walk is
 // issue-bound, so every lane carries TWO consecutive sorted bodies and a warp
 // carries 64 bodies = 64/VOTE vote groups (lanes 8g..8g+7 are group g for
-// VOTE = 16).  A stack entry is {cell, lane mask of the groups that still need
-// it, depth}; a group that accepted a cell is simply absent from the mask of its
-// children.  Per child: one 16-byte octet load, 7 packed fp32 ops for both
-// distances, one ballot (cells only), two MUFU.RSQ, 6 packed ops for the force.
+// VOTE = 16).  A stack entry is {cell - N, one bit per group that still needs the
+// cell | depth << 1}; a group that accepted a cell is simply absent from the
+// mask of its children.  Per pop one LDG.128 brings the cell's walk record (8
+// children + 8 indices, written by summarise) into a per-warp shared-memory row
+// -- per-child global loads miss L1 on every second child (32-byte sectors) and
+// each miss costs an L2 round trip -- and the children are consumed with
+// broadcast LDS.128: child cells first (7 packed fp32 ops, one ballot; a second
+// ballot and the push only if some body is too near), then child bodies.
 constexpr int kForce2Threads = 256;
 constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
 
@@ -498,6 +397,12 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+__device__ __forceinline__ const char *lane_address(const char *base, int rel, int stride) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(rel), "r"(stride), "l"(base));
+    return reinterpret_cast<const char *>(a);
 }
 
 // calculateforce.cl:146-151 for the lane's two bodies; mw = child mass, or 0 for a lane whose group does not use the child
@@ -512,14 +417,13 @@ __device__ __forceinline__ void force_accumulate(float2 dx, float2 dy, float2 dz
 
 template <int VOTE, bool SLICE, bool COUNT>
 __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
-                                                                 const int *__restrict__ child, const int *__restrict__ meta,
+                                                                 const int *__restrict__ oidx, const int *__restrict__ meta,
                                                                  const int *__restrict__ sorted, float4 *__restrict__ velacc,
                                                                  float4 *__restrict__ accSorted, Scalars *sc, int n, int m,
                                                                  int first, int cnt, float thetaMacro, float eps, float dt) {
     __shared__ float dq[kMaxDepth];
-    __shared__ int2 stackA[kForce2Threads / 32][kStackCap];  // {cell, lane mask}
-    __shared__ int stackD[kForce2Threads / 32][kStackCap];   // depth
-    __shared__ float4 stage[kForce2Threads / 32][12];        // the popped cell's row: 8 children, 8 indices, meta
+    __shared__ int2 stack[kForce2Threads / 32][kStackCap];  // {cell - N, group bits | depth << 1}
+    __shared__ float4 stage[kForce2Threads / 32][10];       // the popped cell's walk record: 8 children, 8 indices
     if (sc->error != 0) return;
     const int maxDepth = sc->maxDepth;
     if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
@@ -537,110 +441,122 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     }
     __syncthreads();
     constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kLanesPerGroup = VOTE / 2;  // two bodies per lane
+    constexpr unsigned kGroupLanes = (kLanesPerGroup == 32) ? kFull : ((1u << kLanesPerGroup) - 1u);
+    constexpr unsigned kSpread = (kLanesPerGroup == 8) ? 0x01010101u : (kLanesPerGroup == 16) ? 0x00010001u : 1u;  // first lane of every group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int end = first + cnt;
     const int base = first + (blockIdx.x * (kForce2Threads / 32) + warp) * 64;
     // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
     const int k0 = base + 2 * lane;
     const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
-    constexpr int kLanesPerGroup = VOTE / 2;
     const int gfirst = lane & ~(kLanesPerGroup - 1);  // first lane of my group
-    unsigned gm = ((kLanesPerGroup == 32) ? kFull : ((1u << kLanesPerGroup) - 1u)) << gfirst;
-    asm volatile("" : "+r"(gm));  // keep the group mask in a register (ptxas would rematerialise it per vote)
+    unsigned gm = kGroupLanes << gfirst;              // lanes of my group
+    unsigned gbit = 1u << gfirst;                     // my group's bit in a stack entry
+    asm volatile("" : "+r"(gm), "+r"(gbit));          // keep both in registers (ptxas would rematerialise them per vote)
     // a slot past the end borrows the position of the group's first body: its vote then equals that body's
     const int kg = base + 2 * gfirst;
-    const int s0 = (nact > 0) ? k0 : min(kg, end - 1), s1 = (nact > 1) ? k0 + 1 : s0;
+    const int s0 = (nact > 0) ? k0 : max(0, min(kg, end - 1)), s1 = (nact > 1) ? k0 + 1 : s0;
     const int b0 = sorted[s0], b1 = sorted[s1];
     const float4 p0 = node4[b0], p1 = node4[b1];
     const float2 npx = make_float2(-p0.x, -p1.x), npy = make_float2(-p0.y, -p1.y), npz = make_float2(-p0.z, -p1.z);
     const float2 eps2 = make_float2(eps, eps);
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
     unsigned long long nInter = 0, nOpen = 0;
-    int2 *stA = stackA[warp];
-    int *stD = stackD[warp];
-    // groups with at least one existing body take part in the walk
-    const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
-    unsigned startMask = 0;
-#pragma unroll
-    for (int g = 0; g < 32 / kLanesPerGroup; ++g) {
-        const unsigned m1 = ((kLanesPerGroup == 32) ? kFull : ((1u << kLanesPerGroup) - 1u)) << (g * kLanesPerGroup);
-        if (lanesActive & m1) startMask |= m1;
-    }
-    int sp = 0;
-    stA[0] = make_int2(m, (int)startMask);
-    stD[0] = 0;
-    sp = startMask != 0u ? 1 : 0;
-    // Row fetch: one LDG.128 per pop brings the cell's whole record -- 8 child {x,y,z,m} (lanes 0-7), 8 child
-    // indices (lanes 8-9) and the meta word (lane 10) -- into a per-warp shared-memory row; the children are
-    // then consumed with broadcast LDS.128.  (Per-child global loads miss L1 once per 32-byte sector, i.e. on
-    // every second child, and each miss stalls the warp for an L2 round trip.)
-    const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
-                           : lane < 10 ? reinterpret_cast<const char *>(child) + 16 * (lane - 8)
-                                       : reinterpret_cast<const char *>(meta);
-    const int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+    int2 *stk = stack[warp];
     float4 *row = stage[warp];
     const int *rowInt = reinterpret_cast<const int *>(row);
+    // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices (lane 10 only prefetches the meta word)
+    const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
+                           : lane < 10 ? reinterpret_cast<const char *>(oidx) + 16 * (lane - 8)
+                                       : reinterpret_cast<const char *>(meta);
+    const int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+    // groups with at least one existing body take part in the walk
+    const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
+    unsigned startBits = 0;
+#pragma unroll
+    for (int g = 0; g < 32 / kLanesPerGroup; ++g)
+        if (lanesActive & (kGroupLanes << (g * kLanesPerGroup))) startBits |= 1u << (g * kLanesPerGroup);
+    int sp = 0;
+    if (startBits != 0u) stk[sp++] = make_int2(m - n, (int)startBits);  // depth 0
     while (sp > 0) {
-        --sp;
-        const int2 e = stA[sp];
-        const int d = stD[sp];
-        __syncwarp();  // every lane has read the entry (and is done with the previous row)
-        const int rel = e.x - n;
-        if (lane < 11) {
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(laneBase + (size_t)rel * laneStride) & ~uintptr_t(15);
-            row[lane] = __ldg(reinterpret_cast<const float4 *>(addr));
-        }
-        const unsigned lmask = (unsigned)e.y;
-        const bool mine = (lmask >> lane) & 1u;
-        const unsigned gmMine = mine ? gm : 0u;  // my group's lanes if my group still needs this cell
-        const unsigned notMine = mine ? 0u : kFull;
-        const float thr = dq[d];
-        __syncwarp();
+        const int2 e = stk[--sp];
+        __syncwarp();  // every lane has read the entry and is done with the previous row
+        const int rel = e.x;
+        if (lane < 10) row[lane] = __ldg(reinterpret_cast<const float4 *>(lane_address(laneBase, rel, laneStride)));
         // REDUX puts the (warp-uniform) word into a uniform register: ptxas then knows that the
         // branches on it are uniform and emits no divergence guards around the votes
-        const int mt = __reduce_or_sync(kFull, rowInt[40 + (rel & 3)]);
-        const int nch = mt & 15;
-        const unsigned cmask = (unsigned)mt >> 8;
-#define BH_CHILD(j)                                                                                                  \
-    {                                                                                                                \
-        const float4 c = row[j];                                                                                     \
-        const float2 dx = __fadd2_rn(make_float2(c.x, c.x), npx); /* c - p, exactly */                               \
-        const float2 dy = __fadd2_rn(make_float2(c.y, c.y), npy);                                                    \
-        const float2 dz = __fadd2_rn(make_float2(c.z, c.z), npz);                                                    \
-        const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2); /* :138-143 */ \
-        if ((cmask >> (j)) & 1u) { /* a cell: the group votes (calculateforce.cl:145) */                            \
-            const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr));                               \
-            const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                       \
-            if (open) { /* :154-163 */                                                                               \
-                const int ch = rowInt[32 + (j)];                                                                     \
-                stA[sp] = make_int2(ch, (int)open);                                                                  \
-                stD[sp] = d + 1;                                                                                     \
-                ++sp;                                                                                                \
-                if (lane < 11) prefetch_l1(laneBase + (size_t)(ch - n) * laneStride);                                \
-            }                                                                                                        \
-            const bool use = ((near & gm) | notMine) == 0u;                                                          \
-            if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                       \
-            if (lmask & ~open) { /* at least one group uses the cell as a point mass */                             \
-                force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);                                      \
-                if (COUNT && use) nInter += nact;                                                                    \
-            }                                                                                                        \
-        } else { /* a body: always used (:145 child < NBODIES) */                                                   \
-            force_accumulate(dx, dy, dz, r2, mine ? c.w : 0.0f, ax, ay, az);                                         \
-            if (COUNT && mine) nInter += nact;                                                                       \
-        }                                                                                                            \
+        const int mt = __reduce_or_sync(kFull, __ldg(meta + rel));
+        const unsigned bits = (unsigned)e.y & kSpread;
+        const int dnext = (e.y & 0x7e) + 2;  // (depth + 1) << 1
+        const float thr = dq[(e.y >> 1) & 63];
+        const bool mine = ((unsigned)e.y & gbit) != 0u;
+        const unsigned gmMine = mine ? gm : 0u;  // my group's lanes if my group still needs this cell
+        const unsigned notMine = mine ? 0u : kFull;
+        const float mscale = mine ? 1.0f : 0.0f;
+        const int ncell = mt & 15, nbody = mt >> 4;
+        __syncwarp();
+#define BH_DIST(c)                                                                                                     \
+    const float2 dx = __fadd2_rn(make_float2((c).x, (c).x), npx); /* c - p, exactly */                                 \
+    const float2 dy = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                      \
+    const float2 dz = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                      \
+    const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2); /* :138-143 */
+#define BH_CELL(j)                                                                                                     \
+    {                                                                                                                  \
+        const float4 c = row[j];                                                                                       \
+        BH_DIST(c)                                                                                                     \
+        const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr)); /* the group votes, :145 */         \
+        if (near == 0u) { /* far enough for every body of the warp: every group that is here uses it */               \
+            force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);                                      \
+            if (COUNT && mine) nInter += nact;                                                                         \
+        } else {                                                                                                       \
+            const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                         \
+            if (open) { /* :154-163 */                                                                                 \
+                const int ch = rowInt[32 + (j)];                                                                       \
+                stk[sp++] = make_int2(ch, (int)((open & kSpread) | (unsigned)dnext));                                  \
+                if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));                                    \
+            }                                                                                                          \
+            if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                         \
+            if (bits & ~open) { /* at least one group uses the cell as a point mass */                                \
+                const bool use = ((near & gm) | notMine) == 0u;                                                        \
+                force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);                                        \
+                if (COUNT && use) nInter += nact;                                                                      \
+            }                                                                                                          \
+        }                                                                                                              \
     }
-        switch (nch) {  // children are compacted: evaluate slots nch-1 .. 0, one jump instead of a test per child
-        case 8: BH_CHILD(7)
-        case 7: BH_CHILD(6)
-        case 6: BH_CHILD(5)
-        case 5: BH_CHILD(4)
-        case 4: BH_CHILD(3)
-        case 3: BH_CHILD(2)
-        case 2: BH_CHILD(1)
-        case 1: BH_CHILD(0)
+#define BH_BODY(j)                                                                                                     \
+    { /* a body: always used (:145 child < NBODIES) */                                                                \
+        const float4 c = brow[j];                                                                                      \
+        BH_DIST(c)                                                                                                     \
+        force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);                                          \
+        if (COUNT && mine) nInter += nact;                                                                             \
+    }
+        switch (ncell) {  // one jump instead of a test per child
+        case 8: BH_CELL(7)
+        case 7: BH_CELL(6)
+        case 6: BH_CELL(5)
+        case 5: BH_CELL(4)
+        case 4: BH_CELL(3)
+        case 3: BH_CELL(2)
+        case 2: BH_CELL(1)
+        case 1: BH_CELL(0)
         default: break;
         }
-#undef BH_CHILD
+        const float4 *brow = row + ncell;
+        switch (nbody) {
+        case 8: BH_BODY(7)
+        case 7: BH_BODY(6)
+        case 6: BH_BODY(5)
+        case 5: BH_BODY(4)
+        case 4: BH_BODY(3)
+        case 3: BH_BODY(2)
+        case 2: BH_BODY(1)
+        case 1: BH_BODY(0)
+        default: break;
+        }
+#undef BH_BODY
+#undef BH_CELL
+#undef BH_DIST
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {

@@ -30,7 +30,7 @@ struct Sim {
     cudaStream_t stream = nullptr, ownStream = nullptr;
     // device state
     float4 *node4 = nullptr, *velacc = nullptr, *octet = nullptr, *accSorted = nullptr;
-    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr;
+    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr, *oidx = nullptr;
     float *partials = nullptr;
     bh::Scalars *sc = nullptr;
     bh::Scalars *hostSc = nullptr;  // pinned mirror
@@ -41,7 +41,6 @@ struct Sim {
     // options
     bool profiling = false, counting = false;
     int insertionOrder = 1;
-    int forceVariant = 2;
     bool haveSorted = false;
     // profiling
     cudaEvent_t ev[kProfSteps][BH_NUM_STAGES + 1] = {};
@@ -101,8 +100,7 @@ int resetState(Sim *s) {
 // force walk for sorted slots [first, first+cnt): fused velocity correction (slice = false) or
 // sorted-order acceleration output (slice = true)
 void launchForce(Sim *s, int first, int cnt, bool slice, bool counting) {
-#define BH_FORCE_ARGS1 s->node4, s->octet, s->child, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
-#define BH_FORCE_ARGS2 s->node4, s->octet, s->child, s->meta, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
+#define BH_FORCE_ARGS2 s->node4, s->octet, s->oidx, s->meta, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
 #define BH_FORCE_DISPATCH(KERNEL, THREADS, BODIES, ARGS)                                                     \
     do {                                                                                                     \
         const int grid = (cnt + (BODIES) - 1) / (BODIES);                                                     \
@@ -116,12 +114,8 @@ void launchForce(Sim *s, int first, int cnt, bool slice, bool counting) {
             else KERNEL<32, false, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                            \
         }                                                                                                    \
     } while (0)
-    if (s->forceVariant == 1)
-        BH_FORCE_DISPATCH(bh::force_kernel, bh::kForceThreads, bh::kForceThreads, BH_FORCE_ARGS1);
-    else
-        BH_FORCE_DISPATCH(bh::force2_kernel, bh::kForce2Threads, bh::kForce2Bodies, BH_FORCE_ARGS2);
+    BH_FORCE_DISPATCH(bh::force2_kernel, bh::kForce2Threads, bh::kForce2Bodies, BH_FORCE_ARGS2);
 #undef BH_FORCE_DISPATCH
-#undef BH_FORCE_ARGS1
 #undef BH_FORCE_ARGS2
 }
 
@@ -137,7 +131,7 @@ int launchStage(Sim *s, int stage) {
             s->node4, s->child, s->start, s->count, (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
         break;
     case BH_STAGE_SUMMARIZE:
-        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->meta, s->count,
+        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->oidx, s->meta, s->count,
                                                                               s->sc, n, m);
         break;
     case BH_STAGE_SORT:
@@ -286,7 +280,8 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
-    BH_ALLOC(s->meta, sizeof(int) * (nc + 4));  // +4: the force walk reads the aligned int4 around an entry
+    BH_ALLOC(s->meta, sizeof(int) * nc);
+    BH_ALLOC(s->oidx, sizeof(int) * 8 * nc);
     BH_ALLOC(s->sorted, sizeof(int) * n);
     BH_ALLOC(s->sc, sizeof(bh::Scalars));
 #undef BH_ALLOC
@@ -325,7 +320,7 @@ void bh_destroy(bh_sim *sim) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
-    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta);
+    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta); cudaFree(s->oidx);
     cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
@@ -369,13 +364,6 @@ int bh_set_profiling(bh_sim *sim, int32_t on) {
 int bh_set_counting(bh_sim *sim, int32_t on) {
     BH_ENTER(sim);
     s->counting = on != 0;
-    return BH_OK;
-}
-
-int bh_set_force_variant(bh_sim *sim, int32_t variant) {
-    BH_ENTER(sim);
-    if (variant != 1 && variant != 2) return fail(s, BH_ERR_ARG, "force variant must be 1 or 2");
-    s->forceVariant = variant;
     return BH_OK;
 }
 

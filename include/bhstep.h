@@ -97,9 +97,6 @@ int bh_set_counting(bh_sim *sim, int32_t on);
 /* Order in which build_tree inserts bodies: 0 = index order, 1 = previous step's
  * sorted (DFS / Morton-like) order.  The resulting tree is identical. */
 int bh_set_insertion_order(bh_sim *sim, int32_t mode);
-/* Force-walk kernel: 2 (default) = two bodies per lane on the packed fp32x2 pipe,
- * 1 = one body per lane (scalar fp32).  Same interactions, same votes. */
-int bh_set_force_variant(bh_sim *sim, int32_t variant);
 
 /* createBuffer(CL_MEM_COPY_HOST_PTR, ...) for the seven generator outputs (GPUBH:155-170):
  * caller-owned host SoA arrays of length nbodies are copied; all other buffers are

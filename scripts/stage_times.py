@@ -10,7 +10,6 @@ def run(n, gen, steps=5, warm=3, order=1, vote=16, variant=2):
     sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.ArrayUniverseGenerator(*a), vote_width=vote)
     sim.init(None)
     sim.setInsertionOrder(order)
-    sim.setForceVariant(variant)
     sim.setCounting(True); sim.step(1); st = sim.stats(); sim.setCounting(False)
     inter, opens = st["interactions"], st["opens"]
     sim.step(warm - 1)
@@ -29,8 +28,7 @@ def run(n, gen, steps=5, warm=3, order=1, vote=16, variant=2):
 if __name__ == "__main__":
     sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [32768, 1 << 20]
     for n in sizes:
-        for variant in (1, 2):
-            run(n, U.PlummerUniverseGenerator(42), variant=variant)
+        run(n, U.PlummerUniverseGenerator(42))
     run(1 << 20, U.RandomCubicUniverseGenerator(6.0, 44))
     run(1 << 20, U.PlummerUniverseGenerator(42), vote=32)
     run(1 << 20, U.PlummerUniverseGenerator(42), order=0)
