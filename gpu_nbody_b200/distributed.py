@@ -19,9 +19,6 @@ the all-gather on the engine's sorted-order acceleration buffer.
 """
 from __future__ import annotations
 
-import ctypes as C
-
-from . import _lib
 from .simulation import GPUBarnesHutNBodySimulation
 
 SLICE_ALIGN = 32  # a hardware warp = two 16-body vote groups
@@ -34,8 +31,9 @@ def slice_bounds(nbodies: int, world_size: int, align: int = SLICE_ALIGN):
     chunk = -(-chunk // align) * align
     bounds = []
     for r in range(world_size):
-        first = min(r * chunk, nbodies)
-        bounds.append((first, max(0, min(chunk, nbodies - first))))
+        first = r * chunk
+        count = max(0, min(chunk, nbodies - first))
+        bounds.append((first, count) if count else (0, 0))
     return chunk, bounds
 
 
