@@ -93,8 +93,8 @@ __device__ __forceinline__ void warp_minmax(float &mnx, float &mny, float &mnz, 
 
 __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__ node4, int *__restrict__ child,
                                                             int *__restrict__ start, int *__restrict__ count,
-                                                            float *__restrict__ partials, Scalars *__restrict__ sc,
-                                                            int n, int m) {
+                                                            int *__restrict__ arrived, float *__restrict__ partials,
+                                                            Scalars *__restrict__ sc, int n, int m) {
     __shared__ float red[6][kBboxThreads / 32];
     __shared__ bool isLast;
     const float4 seed = node4[0];  // boundingbox.cl:44-58: every lane starts from body 0
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
         node4[m] = make_float4(rx, ry, rz, -1.0f);
         start[m - n] = 0;
         count[m - n] = -1;
+        arrived[m - n] = 0;
         sc->step = sc->step + 1;
     }
 }
@@ -168,6 +169,7 @@ constexpr int kBuildThreads = 256;
 
 __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict__ node4, int *child,
                                                               int *__restrict__ start, int *__restrict__ count,
+                                                              int *__restrict__ parent, int *__restrict__ arrived,
                                                               const int *__restrict__ order, Scalars *sc, int n, int m) {
     enum { kIdle = 0, kNew, kDescend, kSplit };
     constexpr unsigned kFull = 0xffffffffu;
@@ -252,6 +254,8 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                     node4[cell] = make_float4(cx, cy, cz, -1.0f);
                     start[cell - n] = -1;
                     count[cell - n] = -1;
+                    parent[cell - n] = cur;  // for the counter-driven summarise
+                    arrived[cell - n] = 0;
                     const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
                     const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
                     int *row = child + (size_t)(cell - n) * 8;
@@ -282,84 +286,105 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
 
 // ---- 3. summarise ---------------------------------------------------------------
 // summarizetree.cl: bottom-up centre of mass, body counts, child compaction.
-// One thread per cell, ascending index (children have lower indices than their
-// parent); a thread waits for a child cell's count >= 0.  Children are summed
-// in octant order, which makes the result independent of timing.  Needs every
-// thread of the grid resident (grid sized by occupancy on the host).
+// The reference (and Burtscher's original) walks the cells in ascending index
+// order and spins on children that are not ready; on 10^7 bodies most threads
+// then sit in long parent-child chains.  Here the pass is counter driven and
+// never waits: every cell collects one report per child cell plus one from its
+// own thread (`arrived`, reset at creation); whoever reports last summarises the
+// cell, reports to the parent and climbs on.  Children are summed in octant order,
+// which makes the result independent of timing and bit-identical to the oracle.
+// The summarising thread also writes the force walk's record of the cell.
 constexpr int kSummThreads = 256;
+
+__device__ __forceinline__ int count_child_cells(const int *row, int n) {
+    const int4 lo = __ldcg(reinterpret_cast<const int4 *>(row)), hi = __ldcg(reinterpret_cast<const int4 *>(row) + 1);
+    return (lo.x >= n) + (lo.y >= n) + (lo.z >= n) + (lo.w >= n) + (hi.x >= n) + (hi.y >= n) + (hi.z >= n) + (hi.w >= n);
+}
 
 __global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
                                                                  float4 *__restrict__ octet, int *__restrict__ oidx,
-                                                                 int *__restrict__ meta, int *count, Scalars *sc, int n, int m) {
+                                                                 int *__restrict__ meta, int *__restrict__ count,
+                                                                 const int *__restrict__ parent, int *arrived, Scalars *sc,
+                                                                 int n, int m) {
     if (sc->error != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->bottom = m;  // buildtree.cl:117
         return;
     }
     const int bottom = sc->bottom;
     const int stride = gridDim.x * blockDim.x;
-    for (int cell = bottom + blockIdx.x * blockDim.x + threadIdx.x; cell <= m; cell += stride) {
-        int *row = child + (size_t)(cell - n) * 8;
-        const int4 lo = reinterpret_cast<const int4 *>(row)[0], hi = reinterpret_cast<const int4 *>(row)[1];
-        const int in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        int out[8];
-        int used = 0;
+    for (int first = bottom + blockIdx.x * blockDim.x + threadIdx.x; first <= m; first += stride) {
+        int cell = first;
+        // a cell is summarised by whoever arrives last among its child cells and its own thread; its row stays
+        // untouched until then, so counting the child cells here cannot race with the compaction below
+        if (atomicAdd(arrived + (cell - n), 1) != count_child_cells(child + (size_t)(cell - n) * 8, n)) continue;
+        __threadfence();
+        for (;;) {
+            int *row = child + (size_t)(cell - n) * 8;
+            const int4 lo = __ldcg(reinterpret_cast<const int4 *>(row)), hi = __ldcg(reinterpret_cast<const int4 *>(row) + 1);
+            const int in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            int out[8];
+            int used = 0, ncell = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out[k] = -1;
+            for (int k = 0; k < 8; ++k) out[k] = -1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // summarizetree.cl:77-81 compaction, octant order kept
-            if (in[k] >= 0) {
+            for (int k = 0; k < 8; ++k)  // summarizetree.cl:77-81 compaction, octant order kept
+                if (in[k] >= 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j == used) out[j] = in[k];
-                ++used;
-            }
-        float cm = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
-        int bodies = used;  // summarizetree.cl:118
-        bool ok = true;
-        // walk record of this cell for the force kernel: child cells first, then child bodies
-        float4 *orow = octet + (size_t)(cell - n) * 8;
-        int *irow = oidx + (size_t)(cell - n) * 8;
-        int ncell = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ncell += (out[k] >= n) ? 1 : 0;
-        int cpos = 0, bpos = ncell;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int ch = out[k];
-            if (ch < 0) break;
-            float4 c;
-            if (ch >= n) {
-                int cnt, spins = 0;
-                while ((cnt = ld_acquire(count + (ch - n))) < 0) {
-                    if ((++spins & 255) == 0 && (spins > kSpinBudget || *reinterpret_cast<volatile int *>(&sc->error) != 0)) {
-                        ok = false;
-                        break;
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        if (j == used) out[j] = in[k];
+                    ++used;
+                    ncell += in[k] >= n;
                 }
-                if (!ok) break;
-                bodies += cnt - 1;  // summarizetree.cl:98-105
-                c = __ldcg(node4 + ch);
-                irow[cpos] = ch - n;
-                orow[cpos++] = c;
-            } else {
-                c = node4[ch];
-                orow[bpos++] = c;
+            // all child records are final (child cells reported before this thread got here): fetch them together
+            float4 c[8];
+            int cnt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                c[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                cnt[k] = 0;
+                if (out[k] >= n) {
+                    c[k] = __ldcg(node4 + out[k]);
+                    cnt[k] = __ldcg(count + (out[k] - n));
+                } else if (out[k] >= 0) {
+                    c[k] = node4[out[k]];
+                    cnt[k] = 1;
+                }
             }
-            cm = __fadd_rn(cm, c.w);  // summarizetree.cl:107-110
-            cx = fmaf(c.x, c.w, cx);
-            cy = fmaf(c.y, c.w, cy);
-            cz = fmaf(c.z, c.w, cz);
+            float cm = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
+            int bodies = 0;  // summarizetree.cl:98-105,118
+            float4 *orow = octet + (size_t)(cell - n) * 8;
+            int *irow = oidx + (size_t)(cell - n) * 8;
+            int cpos = 0, bpos = ncell;  // the force walk's record: child cells first, then child bodies
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (out[k] < 0) break;
+                bodies += cnt[k];
+                cm = __fadd_rn(cm, c[k].w);  // summarizetree.cl:107-110, octant order
+                cx = fmaf(c[k].x, c[k].w, cx);
+                cy = fmaf(c[k].y, c[k].w, cy);
+                cz = fmaf(c[k].z, c[k].w, cz);
+                if (out[k] >= n) {
+                    irow[cpos] = out[k] - n;
+                    orow[cpos++] = c[k];
+                } else {
+                    orow[bpos++] = c[k];
+                }
+            }
+            reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
+            reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
+            meta[cell - n] = ncell | ((used - ncell) << 4);  // force walk: #child cells, #child bodies
+            const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
+            __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
+            __stcg(count + (cell - n), bodies);  // summarizetree.cl:160
+            if (cell == m) break;                // the root
+            // report to the parent; the child that reports last continues with it
+            const int par = parent[cell - n];
+            const int need = count_child_cells(child + (size_t)(par - n) * 8, n);
+            __threadfence();  // summarizetree.cl:170: this cell's record before the report
+            if (atomicAdd(arrived + (par - n), 1) != need) break;  // need child cells + the parent's own thread
+            __threadfence();
+            cell = par;
         }
-        if (!ok) {
-            atomicCAS(&sc->error, 0, 2);
-            return;
-        }
-        reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
-        reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
-        meta[cell - n] = ncell | ((used - ncell) << 4);  // force walk: #child cells, #child bodies
-        const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
-        __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
-        st_release(count + (cell - n), bodies);  // summarizetree.cl:160,170-172: data first, flag last
     }
 }
 

@@ -30,7 +30,7 @@ struct Sim {
     cudaStream_t stream = nullptr, ownStream = nullptr;
     // device state
     float4 *node4 = nullptr, *velacc = nullptr, *octet = nullptr, *accSorted = nullptr;
-    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr, *oidx = nullptr;
+    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr, *oidx = nullptr, *parent = nullptr, *arrived = nullptr;
     float *partials = nullptr;
     bh::Scalars *sc = nullptr;
     bh::Scalars *hostSc = nullptr;  // pinned mirror
@@ -123,16 +123,17 @@ int launchStage(Sim *s, int stage) {
     const int n = s->n, m = s->m;
     switch (stage) {
     case BH_STAGE_BBOX:
-        bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->node4, s->child, s->start, s->count,
+        bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->node4, s->child, s->start, s->count, s->arrived,
                                                                          s->partials, s->sc, n, m);
         break;
     case BH_STAGE_BUILD:
         bh::build_kernel<<<s->buildGrid, bh::kBuildThreads, 0, s->stream>>>(
-            s->node4, s->child, s->start, s->count, (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
+            s->node4, s->child, s->start, s->count, s->parent, s->arrived,
+            (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
         break;
     case BH_STAGE_SUMMARIZE:
         bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->oidx, s->meta, s->count,
-                                                                              s->sc, n, m);
+                                                                              s->parent, s->arrived, s->sc, n, m);
         break;
     case BH_STAGE_SORT:
         bh::sort_kernel<<<s->sortGrid, bh::kSortThreads, 0, s->stream>>>(s->child, s->count, s->start, s->sorted, s->sc, n, m);
@@ -282,6 +283,8 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->count, sizeof(int) * nc);
     BH_ALLOC(s->meta, sizeof(int) * nc);
     BH_ALLOC(s->oidx, sizeof(int) * 8 * nc);
+    BH_ALLOC(s->parent, sizeof(int) * nc);
+    BH_ALLOC(s->arrived, sizeof(int) * nc);
     BH_ALLOC(s->sorted, sizeof(int) * n);
     BH_ALLOC(s->sc, sizeof(bh::Scalars));
 #undef BH_ALLOC
@@ -320,7 +323,7 @@ void bh_destroy(bh_sim *sim) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
-    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta); cudaFree(s->oidx);
+    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta); cudaFree(s->oidx); cudaFree(s->parent); cudaFree(s->arrived);
     cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
