@@ -201,9 +201,13 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
             while (ch >= n) {  // buildtree.cl:77-89: follow the path to a leaf slot
                 node = ch;
                 ++depth;
+                // the child's centre is recomputed, not loaded: same operands and operations as when the cell
+                // was created (buildtree.cl:124-136), hence the same bits -- one dependent load per level less
+                const float ox = (path & 1) ? r : 0.0f, oy = (path & 2) ? r : 0.0f, oz = (path & 4) ? r : 0.0f;
                 r *= 0.5f;
-                const float4 c = __ldcg(node4 + node);
-                cx = c.x; cy = c.y; cz = c.z;
+                cx = __fadd_rn(__fsub_rn(cx, r), ox);
+                cy = __fadd_rn(__fsub_rn(cy, r), oy);
+                cz = __fadd_rn(__fsub_rn(cz, r), oz);
                 path = octant(cx, cy, cz, p.x, p.y, p.z);
                 slot = child + ((size_t)(node - n) * 8 + path);
                 ch = ld_relaxed(slot);
@@ -301,7 +305,7 @@ __device__ __forceinline__ int count_child_cells(const int *row, int n) {
     return (lo.x >= n) + (lo.y >= n) + (lo.z >= n) + (lo.w >= n) + (hi.x >= n) + (hi.y >= n) + (hi.z >= n) + (hi.w >= n);
 }
 
-__global__ void __launch_bounds__(kSummThreads) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
+__global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
                                                                  float4 *__restrict__ octet, int *__restrict__ oidx,
                                                                  int *__restrict__ meta, int *__restrict__ count,
                                                                  const int *__restrict__ parent, int *arrived, Scalars *sc,
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restric
     const int stride = gridDim.x * blockDim.x;
     for (int cell = m - (blockIdx.x * blockDim.x + threadIdx.x); cell >= bottom; cell -= stride) {
         int s, spins = 0;
-        while ((s = ld_acquire(start + (cell - n))) < 0) {  // sort.cl:36-39
+        while ((s = ld_relaxed(start + (cell - n))) < 0) {  // sort.cl:36-39 (start is the only datum passed: no fence needed)
             if ((++spins & 255) == 0 && (spins > kSpinBudget || *reinterpret_cast<volatile int *>(&sc->error) != 0)) {
                 atomicCAS(&sc->error, 0, 2);
                 return;
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restric
         for (int k = 0; k < 8; ++k) {
             if (ch[k] < 0) break;  // compacted
             if (ch[k] >= n) {      // sort.cl:44-56
-                st_release(start + (ch[k] - n), s);
+                st_relaxed(start + (ch[k] - n), s);
                 s += count[ch[k] - n];
             } else {               // sort.cl:59-65
                 sorted[s++] = ch[k];

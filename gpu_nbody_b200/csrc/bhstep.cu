@@ -296,13 +296,11 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     if ((e = cudaMalloc(reinterpret_cast<void **>(&s->partials), sizeof(float) * 6 * s->bboxGrid)) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMalloc partials", e);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::build_kernel, bh::kBuildThreads, 0);
     s->buildGrid = (int)std::min<size_t>((n + bh::kBuildThreads - 1) / bh::kBuildThreads, (size_t)s->numSMs * std::max(perSM, 1));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::summarize_kernel, bh::kSummThreads, 0);
-    s->summGrid = s->numSMs * std::max(perSM, 1);
+    s->summGrid = (int)std::min<size_t>((nc + bh::kSummThreads - 1) / bh::kSummThreads, (size_t)s->numSMs * 64);  // never waits: any grid
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::sort_kernel, bh::kSortThreads, 0);
     s->sortGrid = s->numSMs * std::max(perSM, 1);
     // tiny problems: do not launch more waiting threads than there can be cells
     const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
-    s->summGrid = std::max(1, std::min(s->summGrid, cellBlocks));
     s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
     if ((e = cudaMemsetAsync(s->node4, 0, sizeof(float4) * ((size_t)m + 1), s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
     cudaMemsetAsync(s->velacc, 0, sizeof(float4) * 2 * n, s->stream);
