@@ -459,6 +459,20 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     return r;
 }
 
+// shared memory through explicit 32-bit shared-window addresses
+__device__ __forceinline__ void lds_v2(unsigned a, int &x, int &y) { asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a) : "memory"); }
+__device__ __forceinline__ void sts_v2(unsigned a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ float4 lds_v4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(unsigned a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+
 __device__ __forceinline__ const char *lane_address(const char *base, int rel, int stride) {
     unsigned long long a;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(rel), "r"(stride), "l"(base));
@@ -523,36 +537,43 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     const float2 eps2 = make_float2(eps, eps);
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
     unsigned long long nInter = 0, nOpen = 0;
-    int2 *stk = stack[warp];
-    float4 *row = stage[warp];
-    const int *rowInt = reinterpret_cast<const int *>(row);
+    // Shared memory is addressed through 32-bit shared-window addresses kept in registers (ptxas otherwise
+    // rebuilds the window base from SR_CgaCtaId on every pop).
+    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(stack[warp]);
+    unsigned rowBase = (unsigned)__cvta_generic_to_shared(stage[warp]);
+    unsigned dqBase = (unsigned)__cvta_generic_to_shared(dq);
+    unsigned rowLane = rowBase + 16u * (unsigned)lane;
     // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices (lane 10 only prefetches the meta word)
     const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
                            : lane < 10 ? reinterpret_cast<const char *>(oidx) + 16 * (lane - 8)
                                        : reinterpret_cast<const char *>(meta);
-    const int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+    int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+    asm volatile("" : "+r"(rowBase), "+r"(dqBase), "+r"(rowLane), "+r"(laneStride));  // keep them in registers
     // groups with at least one existing body take part in the walk
     const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
     unsigned startBits = 0;
 #pragma unroll
     for (int g = 0; g < 32 / kLanesPerGroup; ++g)
         if (lanesActive & (kGroupLanes << (g * kLanesPerGroup))) startBits |= 1u << (g * kLanesPerGroup);
-    int sp = 0;
-    if (startBits != 0u) stk[sp++] = make_int2(m - n, (int)startBits);  // depth 0
-    while (sp > 0) {
-        const int2 e = stk[--sp];
+    unsigned sp = stkBase;  // address of the first free stack slot
+    if (startBits != 0u) {
+        sts_v2(sp, m - n, (int)startBits);  // depth 0
+        sp += 8;
+    }
+    while (sp != stkBase) {
+        sp -= 8;
+        int rel, ey;
+        lds_v2(sp, rel, ey);
         __syncwarp();  // every lane has read the entry and is done with the previous row
-        const int rel = e.x;
-        if (lane < 10) row[lane] = __ldg(reinterpret_cast<const float4 *>(lane_address(laneBase, rel, laneStride)));
+        if (lane < 10) sts_v4(rowLane, __ldg(reinterpret_cast<const float4 *>(lane_address(laneBase, rel, laneStride))));
         // REDUX puts the (warp-uniform) word into a uniform register: ptxas then knows that the
         // branches on it are uniform and emits no divergence guards around the votes
         const int mt = __reduce_or_sync(kFull, __ldg(meta + rel));
-        const unsigned bits = (unsigned)e.y & kSpread;
-        const int dnext = (e.y & 0x7e) + 2;  // (depth + 1) << 1
-        const float thr = dq[(e.y >> 1) & 63];
-        const bool mine = ((unsigned)e.y & gbit) != 0u;
+        const unsigned bits = (unsigned)ey & kSpread;
+        const int dnext = (ey & 0x7e) + 2;  // (depth + 1) << 1
+        const float thr = lds_f32(dqBase + ((unsigned)(ey & 0x7e) << 1));
+        const bool mine = ((unsigned)ey & gbit) != 0u;
         const unsigned gmMine = mine ? gm : 0u;  // my group's lanes if my group still needs this cell
-        const unsigned notMine = mine ? 0u : kFull;
         const float mscale = mine ? 1.0f : 0.0f;
         const int ncell = mt & 15, nbody = mt >> 4;
         __syncwarp();
@@ -561,61 +582,40 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     const float2 dy = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                      \
     const float2 dz = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                      \
     const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2); /* :138-143 */
-#define BH_CELL(j)                                                                                                     \
-    {                                                                                                                  \
-        const float4 c = row[j];                                                                                       \
-        BH_DIST(c)                                                                                                     \
-        const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr)); /* the group votes, :145 */         \
-        if (near == 0u) { /* far enough for every body of the warp: every group that is here uses it */               \
-            force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);                                      \
-            if (COUNT && mine) nInter += nact;                                                                         \
-        } else {                                                                                                       \
-            const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                         \
-            if (open) { /* :154-163 */                                                                                 \
-                const int ch = rowInt[32 + (j)];                                                                       \
-                stk[sp++] = make_int2(ch, (int)((open & kSpread) | (unsigned)dnext));                                  \
-                if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));                                    \
-            }                                                                                                          \
-            if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                         \
-            if (bits & ~open) { /* at least one group uses the cell as a point mass */                                \
-                const bool use = ((near & gm) | notMine) == 0u;                                                        \
-                force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);                                        \
-                if (COUNT && use) nInter += nact;                                                                      \
-            }                                                                                                          \
-        }                                                                                                              \
-    }
-#define BH_BODY(j)                                                                                                     \
-    { /* a body: always used (:145 child < NBODIES) */                                                                \
-        const float4 c = brow[j];                                                                                      \
-        BH_DIST(c)                                                                                                     \
-        force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);                                          \
-        if (COUNT && mine) nInter += nact;                                                                             \
-    }
-        switch (ncell) {  // one jump instead of a test per child
-        case 8: BH_CELL(7)
-        case 7: BH_CELL(6)
-        case 6: BH_CELL(5)
-        case 5: BH_CELL(4)
-        case 4: BH_CELL(3)
-        case 3: BH_CELL(2)
-        case 2: BH_CELL(1)
-        case 1: BH_CELL(0)
-        default: break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // child cells come first
+            if (j >= ncell) break;
+            const float4 c = lds_v4(rowBase + 16u * j);
+            BH_DIST(c)
+            const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr));  // the group votes, :145
+            if (near == 0u) {  // far enough for every body of the warp: every group that is here uses it
+                force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);
+                if (COUNT && mine) nInter += nact;
+            } else {
+                const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);
+                if (open) {  // :154-163
+                    const int ch = lds_s32(rowBase + 128u + 4u * j);
+                    sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));
+                    sp += 8;
+                    if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));
+                }
+                if (COUNT && (near & gmMine) != 0u) nOpen += nact;
+                if (bits & ~open) {  // at least one group uses the cell as a point mass
+                    const bool use = mine && (near & gm) == 0u;
+                    force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);
+                    if (COUNT && use) nInter += nact;
+                }
+            }
         }
-        const float4 *brow = row + ncell;
-        switch (nbody) {
-        case 8: BH_BODY(7)
-        case 7: BH_BODY(6)
-        case 6: BH_BODY(5)
-        case 5: BH_BODY(4)
-        case 4: BH_BODY(3)
-        case 3: BH_BODY(2)
-        case 2: BH_BODY(1)
-        case 1: BH_BODY(0)
-        default: break;
+        const unsigned brow = rowBase + 16u * (unsigned)ncell;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // then child bodies: always used (:145 child < NBODIES)
+            if (j >= nbody) break;
+            const float4 c = lds_v4(brow + 16u * j);
+            BH_DIST(c)
+            force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);
+            if (COUNT && mine) nInter += nact;
         }
-#undef BH_BODY
-#undef BH_CELL
 #undef BH_DIST
     }
     if (COUNT) {
