@@ -60,7 +60,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = build()
+    path = os.environ.get("BHSTEP_LIBRARY") or build()  # BHSTEP_LIBRARY: an alternative build of the same sources (kernel experiments)
     lib = C.CDLL(path)
     p, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     protos = {

@@ -587,11 +587,12 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             if (j >= ncell) break;
             const float4 c = lds_v4(rowBase + 16u * j);
             BH_DIST(c)
-            const unsigned near = __ballot_sync(kFull, !(r2.x >= thr && r2.y >= thr));  // the group votes, :145
-            if (near == 0u) {  // far enough for every body of the warp: every group that is here uses it
+            const bool far = r2.x >= thr && r2.y >= thr;  // the group votes, :145
+            if (__all_sync(kFull, far)) {  // far enough for every body of the warp: every group that is here uses it
                 force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);
                 if (COUNT && mine) nInter += nact;
             } else {
+                const unsigned near = __ballot_sync(kFull, !far);
                 const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);
                 if (open) {  // :154-163
                     const int ch = lds_s32(rowBase + 128u + 4u * j);
