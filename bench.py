@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
         C = st["cells_used"]
         alg = {"bounding_box": 12 * n, "build_tree": 16 * n + 52 * C, "summarize": 16 * n + 104 * C, "sort": 4 * n + 44 * C,
                "integrate": 60 * n}
-        line["roofline"] = {"kernel": "force_kernel<16,false,false>", "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        line["roofline"] = {"kernel": "force2_kernel<16,false,false>", "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                             "flops_per_launch": flops, "interactions_per_body": inter / n, "opens_per_body": opens / n,
                             "ms_per_launch": f_ms, "share_of_step": f_ms / sum(stage_ms.values())}

@@ -158,51 +158,78 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
 // numbers depend on the allocation race (as in the reference).  Bodies are
 // visited through `order` (previous step's sorted[] = spatial order) when given.
 //
-// Every lane is a small state machine (NEW -> DESCEND -> SPLIT -> NEW ...) and the
-// warp meets once per round: all lanes that hold a lock and need a cell take them
-// from ONE atomicSub on `bottom` (warp-aggregated, exact and gap-free).  With one
-// atomic per cell the single counter serialises ~0.48 N same-address atomics
-// (about 2 ms at N = 10^7); aggregated it is one per round.  Indices still
-// decrease in allocation order, so a child cell always has a lower index than its
-// parent, which summarise and sort rely on.
+// B200 design, all of it about latency (the kernel issues < 20 % of its slots):
+//  * Every lane owns a contiguous run of the insertion order, so the body it
+//    inserts next is its spatial neighbour.  The lane remembers the path of its
+//    previous body (cells never move or disappear during a build) and replays it
+//    without touching memory -- the octant tests use centres recomputed with the
+//    creation formula, same operands, same bits -- so only the last level or two
+//    are dependent loads.  Lanes of a warp are a run apart: few lock conflicts.
+//  * The warp meets once per round.  A lane that won a lock on an occupied leaf
+//    first counts, in registers, how many cells separate the two bodies; all such
+//    lanes then take their cells from ONE atomicSub on `bottom` (warp-aggregated,
+//    exact and gap-free; one atomic per cell serialised ~0.48 N same-address
+//    atomics, about 2 ms at N = 10^7) and build their whole chain in that round.
+//    Indices still decrease in allocation order, so a child cell always has a
+//    lower index than its parent, which sort relies on.
 constexpr int kBuildThreads = 256;
 
 __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict__ node4, int *child,
                                                               int *__restrict__ start, int *__restrict__ count,
                                                               int *__restrict__ parent, int *__restrict__ arrived,
                                                               const int *__restrict__ order, Scalars *sc, int n, int m) {
-    enum { kIdle = 0, kNew, kDescend, kSplit };
     constexpr unsigned kFull = 0xffffffffu;
     const float radius = sc->radius;
     const float4 root = node4[m];
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int state = i < n ? kNew : kIdle;
+    const int threadsTotal = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int run = (n + threadsTotal - 1) / threadsTotal;  // bodies per lane
+    int i = tid * run;
+    const int iEnd = min(n, i + run);
+    bool busy = i < iEnd;   // this lane still has bodies to insert
+    bool fresh = true;      // the next round starts a new body
     int localMaxDepth = 1, spins = 0;
-    // per-lane insertion state
+    int pathNode[kMaxDepth + 1];           // pathNode[d-1] = cell at depth d of the remembered path (pathNode[0] = root)
+    unsigned char pathOct[kMaxDepth + 1];  // pathOct[d-1] = octant taken from that cell to the next one
+    int pathLen = 1;                       // valid entries of pathNode
+    pathNode[0] = m;
     int body = 0, node = m, depth = 1, path = 0;
-    float4 p = root, q = root;
+    float4 p = root;
     float r = radius, cx = root.x, cy = root.y, cz = root.z;
-    int *slot = child, oldBody = -1, patch = -1, cur = m, curPath = 0;
-    bool abort = false;
     for (;;) {
-        if (state == kNew) {
-            body = order ? order[i] : i;
-            p = node4[body];
-            node = m; depth = 1; r = radius;
-            cx = root.x; cy = root.y; cz = root.z;
-            path = octant(cx, cy, cz, p.x, p.y, p.z);
-            state = kDescend;
-        }
-        if (state == kDescend) {
+        int need = 0;        // cells this lane must allocate in this round
+        int oldBody = -1;
+        int *slot = child;
+        float4 q = root;
+        if (busy) {
+            if (fresh) {
+                body = order ? order[i] : i;
+                p = node4[body];
+                node = m; depth = 1; r = radius;
+                cx = root.x; cy = root.y; cz = root.z;
+                path = octant(cx, cy, cz, p.x, p.y, p.z);
+                // replay the remembered path while the new body takes the same octants
+                while (depth < pathLen && pathOct[depth - 1] == path) {
+                    const float ox = (path & 1) ? r : 0.0f, oy = (path & 2) ? r : 0.0f, oz = (path & 4) ? r : 0.0f;
+                    r *= 0.5f;
+                    cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:124-136
+                    cy = __fadd_rn(__fsub_rn(cy, r), oy);
+                    cz = __fadd_rn(__fsub_rn(cz, r), oz);
+                    node = pathNode[depth];
+                    ++depth;
+                    path = octant(cx, cy, cz, p.x, p.y, p.z);
+                }
+                pathLen = depth;
+                fresh = false;
+            }
             slot = child + ((size_t)(node - n) * 8 + path);
             int ch = ld_relaxed(slot);
             while (ch >= n) {  // buildtree.cl:77-89: follow the path to a leaf slot
+                pathOct[depth - 1] = (unsigned char)path;
+                pathNode[depth] = ch;
                 node = ch;
                 ++depth;
-                // the child's centre is recomputed, not loaded: same operands and operations as when the cell
-                // was created (buildtree.cl:124-136), hence the same bits -- one dependent load per level less
                 const float ox = (path & 1) ? r : 0.0f, oy = (path & 2) ? r : 0.0f, oz = (path & 4) ? r : 0.0f;
                 r *= 0.5f;
                 cx = __fadd_rn(__fsub_rn(cx, r), ox);
@@ -212,77 +239,100 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                 slot = child + ((size_t)(node - n) * 8 + path);
                 ch = ld_relaxed(slot);
             }
+            pathLen = depth;
             if (ch != kLock && atomicCAS(slot, ch, kLock) == ch) {
                 if (ch == -1) {
                     st_relaxed(slot, body);  // buildtree.cl:98-101
                     localMaxDepth = max(localMaxDepth, depth);
-                    i += stride;
-                    state = i < n ? kNew : kIdle;
-                } else {  // buildtree.cl:102-180: split until the two bodies separate, one cell per round
+                    fresh = true;
+                    busy = ++i < iEnd;
+                } else {  // buildtree.cl:102-180: count the cells that separate the two bodies
                     oldBody = ch;
                     q = node4[ch];
-                    patch = -1;
-                    cur = node;
-                    curPath = path;
-                    state = kSplit;
+                    float tr = r, tx = cx, ty = cy, tz = cz;
+                    int tp = path;
+                    for (;;) {
+                        ++need;
+                        const float ox = (tp & 1) ? tr : 0.0f, oy = (tp & 2) ? tr : 0.0f, oz = (tp & 4) ? tr : 0.0f;
+                        tr *= 0.5f;
+                        tx = __fadd_rn(__fsub_rn(tx, tr), ox);
+                        ty = __fadd_rn(__fsub_rn(ty, tr), oy);
+                        tz = __fadd_rn(__fsub_rn(tz, tr), oz);
+                        tp = octant(tx, ty, tz, p.x, p.y, p.z);
+                        if (tp != octant(tx, ty, tz, q.x, q.y, q.z) || depth + need > kMaxDepth) break;
+                    }
                 }
             } else if (ch == kLock && (++spins & 63) == 0) {
-                if (*reinterpret_cast<volatile int *>(&sc->error) != 0) abort = true;
-                if (spins > kSpinBudget) { atomicCAS(&sc->error, 0, 2); abort = true; }
+                if (*reinterpret_cast<volatile int *>(&sc->error) != 0) busy = false;
+                if (spins > kSpinBudget) { atomicCAS(&sc->error, 0, 2); busy = false; }
             }
         }
         // ---- the warp meets: aggregated cell allocation -------------------------------------------------
-        const unsigned need = __ballot_sync(kFull, state == kSplit);
-        if (need != 0u) {
-            const int leader = __ffs(need) - 1;
+        if (__any_sync(kFull, need != 0)) {
+            int incl = need;  // inclusive prefix sum over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(kFull, incl, 31);
             int top = 0;
-            if (lane == leader) top = atomicSub(&sc->bottom, __popc(need));  // buildtree.cl:109, once for the warp
-            top = __shfl_sync(kFull, top, leader);
-            if (state == kSplit) {
-                const int cell = top - 1 - __popc(need & ((1u << lane) - 1u));
-                ++depth;
-                if (cell <= n || depth > kMaxDepth) {  // buildtree.cl:112-119 / calculateforce.cl:69-73
+            if (lane == 0) top = atomicSub(&sc->bottom, total);  // buildtree.cl:109, once for the warp
+            top = __shfl_sync(kFull, top, 0);
+            if (need != 0) {
+                int cell = top - 1 - (incl - need);  // this lane's cells: cell, cell-1, ..., cell-need+1
+                if (cell - need + 1 <= n || depth + need > kMaxDepth) {  // buildtree.cl:112-119 / calculateforce.cl:69-73
                     sc->error = 1;
                     __threadfence();
                     st_relaxed(slot, oldBody);  // give the leaf back so that nobody spins on it
-                    abort = true;
+                    busy = false;
                 } else {
-                    patch = max(patch, cell);
-                    const float ox = (curPath & 1) ? r : 0.0f;  // buildtree.cl:124-126
-                    const float oy = (curPath & 2) ? r : 0.0f;
-                    const float oz = (curPath & 4) ? r : 0.0f;
-                    r *= 0.5f;
-                    cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:134-136, left to right
-                    cy = __fadd_rn(__fsub_rn(cy, r), oy);
-                    cz = __fadd_rn(__fsub_rn(cz, r), oz);
-                    node4[cell] = make_float4(cx, cy, cz, -1.0f);
-                    start[cell - n] = -1;
-                    count[cell - n] = -1;
-                    parent[cell - n] = cur;  // for the counter-driven summarise
-                    arrived[cell - n] = 0;
-                    const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
-                    const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
-                    int *row = child + (size_t)(cell - n) * 8;
-                    const int4 empty = make_int4(-1, -1, -1, -1);
-                    reinterpret_cast<int4 *>(row)[0] = empty;
-                    reinterpret_cast<int4 *>(row)[1] = empty;
-                    if (cell != patch) child[(size_t)(cur - n) * 8 + curPath] = cell;  // :141-146
-                    cur = cell;
-                    curPath = pPath;
-                    if (qPath != pPath) {
-                        row[qPath] = oldBody;      // :152
-                        row[pPath] = body;         // :169
-                        __threadfence();           // :173 publish the sub-tree ...
-                        st_relaxed(slot, patch);   // :180 ... by replacing the lock
-                        localMaxDepth = max(localMaxDepth, depth);
-                        i += stride;
-                        state = i < n ? kNew : kIdle;
+                    const int patch = cell;
+                    int cur = node, curPath = path;
+                    for (;;) {
+                        ++depth;
+                        const float ox = (curPath & 1) ? r : 0.0f;  // buildtree.cl:124-126
+                        const float oy = (curPath & 2) ? r : 0.0f;
+                        const float oz = (curPath & 4) ? r : 0.0f;
+                        r *= 0.5f;
+                        cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:134-136, left to right
+                        cy = __fadd_rn(__fsub_rn(cy, r), oy);
+                        cz = __fadd_rn(__fsub_rn(cz, r), oz);
+                        node4[cell] = make_float4(cx, cy, cz, -1.0f);
+                        start[cell - n] = -1;
+                        count[cell - n] = -1;
+                        parent[cell - n] = cur;  // for the counter-driven summarise
+                        arrived[cell - n] = 0;
+                        const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
+                        const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
+                        int *row = child + (size_t)(cell - n) * 8;
+                        const int4 empty = make_int4(-1, -1, -1, -1);
+                        reinterpret_cast<int4 *>(row)[0] = empty;
+                        reinterpret_cast<int4 *>(row)[1] = empty;
+                        if (cell != patch) child[(size_t)(cur - n) * 8 + curPath] = cell;  // :141-146
+                        pathOct[depth - 2] = (unsigned char)curPath;  // the new cell joins the remembered path
+                        pathNode[depth - 1] = cell;
+                        cur = cell;
+                        curPath = pPath;
+                        if (qPath != pPath) {
+                            row[qPath] = oldBody;  // :152
+                            row[pPath] = body;     // :169
+                            break;
+                        }
+                        --cell;
                     }
+                    pathLen = depth;
+                    node = cur;
+                    path = curPath;
+                    __threadfence();          // :173 publish the sub-tree ...
+                    st_relaxed(slot, patch);  // :180 ... by replacing the lock
+                    localMaxDepth = max(localMaxDepth, depth);
+                    fresh = true;
+                    busy = ++i < iEnd;
                 }
             }
         }
-        if (abort) state = kIdle;
-        if (!__any_sync(kFull, state != kIdle)) break;
+        if (!__any_sync(kFull, busy)) break;
     }
     for (int o = 16; o > 0; o >>= 1) localMaxDepth = max(localMaxDepth, __shfl_xor_sync(kFull, localMaxDepth, o));
     if (lane == 0 && localMaxDepth > 1) atomicMax(&sc->maxDepth, localMaxDepth);  // :199
