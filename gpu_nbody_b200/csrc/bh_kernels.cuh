@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
 //    Indices still decrease in allocation order, so a child cell always has a
 //    lower index than its parent, which sort relies on.
 constexpr int kBuildThreads = 256;
+constexpr int kPathCap = 24;  // remembered levels per lane (24 KB of shared memory per CTA); deeper levels are loaded
 
 __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict__ node4, int *child,
                                                               int *__restrict__ start, int *__restrict__ count,
@@ -190,10 +191,12 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
     bool busy = i < iEnd;   // this lane still has bodies to insert
     bool fresh = true;      // the next round starts a new body
     int localMaxDepth = 1, spins = 0;
-    int pathNode[kMaxDepth + 1];           // pathNode[d-1] = cell at depth d of the remembered path (pathNode[0] = root)
-    unsigned char pathOct[kMaxDepth + 1];  // pathOct[d-1] = octant taken from that cell to the next one
-    int pathLen = 1;                       // valid entries of pathNode
-    pathNode[0] = m;
+    // remembered path of the lane's previous body: the cells at depths 1..pathLen (shared memory, one column per
+    // thread: conflict-free) and the body's position -- its octants are recomputed, not stored
+    __shared__ int pathNode[kPathCap][kBuildThreads];
+    int pathLen = 1;
+    pathNode[0][threadIdx.x] = m;
+    float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;
     int body = 0, node = m, depth = 1, path = 0;
     float4 p = root;
     float r = radius, cx = root.x, cy = root.y, cz = root.z;
@@ -209,25 +212,25 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                 node = m; depth = 1; r = radius;
                 cx = root.x; cy = root.y; cz = root.z;
                 path = octant(cx, cy, cz, p.x, p.y, p.z);
-                // replay the remembered path while the new body takes the same octants
-                while (depth < pathLen && pathOct[depth - 1] == path) {
+                // replay the remembered path while the new body takes the same octants as the previous one
+                while (depth < pathLen && octant(cx, cy, cz, ppx, ppy, ppz) == path) {
                     const float ox = (path & 1) ? r : 0.0f, oy = (path & 2) ? r : 0.0f, oz = (path & 4) ? r : 0.0f;
                     r *= 0.5f;
                     cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:124-136
                     cy = __fadd_rn(__fsub_rn(cy, r), oy);
                     cz = __fadd_rn(__fsub_rn(cz, r), oz);
-                    node = pathNode[depth];
                     ++depth;
                     path = octant(cx, cy, cz, p.x, p.y, p.z);
                 }
+                node = pathNode[depth - 1][threadIdx.x];
                 pathLen = depth;
+                ppx = p.x; ppy = p.y; ppz = p.z;
                 fresh = false;
             }
             slot = child + ((size_t)(node - n) * 8 + path);
             int ch = ld_relaxed(slot);
             while (ch >= n) {  // buildtree.cl:77-89: follow the path to a leaf slot
-                pathOct[depth - 1] = (unsigned char)path;
-                pathNode[depth] = ch;
+                if (depth < kPathCap) pathNode[depth][threadIdx.x] = ch;
                 node = ch;
                 ++depth;
                 const float ox = (path & 1) ? r : 0.0f, oy = (path & 2) ? r : 0.0f, oz = (path & 4) ? r : 0.0f;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                 slot = child + ((size_t)(node - n) * 8 + path);
                 ch = ld_relaxed(slot);
             }
-            pathLen = depth;
+            pathLen = min(depth, kPathCap);
             if (ch != kLock && atomicCAS(slot, ch, kLock) == ch) {
                 if (ch == -1) {
                     st_relaxed(slot, body);  // buildtree.cl:98-101
@@ -310,8 +313,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                         reinterpret_cast<int4 *>(row)[0] = empty;
                         reinterpret_cast<int4 *>(row)[1] = empty;
                         if (cell != patch) child[(size_t)(cur - n) * 8 + curPath] = cell;  // :141-146
-                        pathOct[depth - 2] = (unsigned char)curPath;  // the new cell joins the remembered path
-                        pathNode[depth - 1] = cell;
+                        if (depth <= kPathCap) pathNode[depth - 1][threadIdx.x] = cell;  // the new cell joins the remembered path
                         cur = cell;
                         curPath = pPath;
                         if (qPath != pPath) {
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                         }
                         --cell;
                     }
-                    pathLen = depth;
+                    pathLen = min(depth, kPathCap);
                     node = cur;
                     path = curPath;
                     __threadfence();          // :173 publish the sub-tree ...
