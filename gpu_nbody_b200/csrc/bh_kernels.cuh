@@ -499,7 +499,7 @@ constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 
 // each miss costs an L2 round trip -- and the children are consumed with
 // broadcast LDS.128: child cells first (7 packed fp32 ops, one ballot; a second
 // ballot and the push only if some body is too near), then child bodies.
-constexpr int kForce2Threads = 256;
+constexpr int kForce2Threads = 128;
 constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
