@@ -252,12 +252,21 @@ def run_ours(args, rank, world, local_rank):
         C = st["cells_used"]
         alg = {"bounding_box": 12 * n, "build_tree": 16 * n + 52 * C, "summarize": 16 * n + 104 * C, "sort": 4 * n + 44 * C,
                "integrate": 60 * n}
+        traffic = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this very workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if n == 10_000_000 and args.dist == "plummer":
+                traffic = {k.split("<")[0]: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}
+        except Exception:
+            pass
         line["roofline"] = {"kernel": "force2_kernel<16,false,false>", "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / peak, "traffic": traffic.get("force2_kernel"), "peak_source": peak_src,
                             "flops_per_launch": flops, "interactions_per_body": inter / n, "opens_per_body": opens / n,
                             "ms_per_launch": f_ms, "share_of_step": f_ms / sum(stage_ms.values())}
+        kname = {"bounding_box": "bbox_kernel", "build_tree": "build_kernel", "summarize": "summarize_kernel", "sort": "sort_kernel",
+                 "integrate": "integrate_kernel"}
         line["stages"] = {k: {"ms": stage_ms[k], "bound": "hbm", "alg_bytes": alg[k], "achieved_gbs": alg[k] / (stage_ms[k] * 1e-3) / 1e9,
-                              "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak} for k in alg}
+                              "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get(kname[k])} for k in alg}
         line["stages"]["hbm_peak_gbs"] = hbm_peak
         line["stages"]["hbm_peak_source"] = hbm_src
         if not args.no_cpu:
