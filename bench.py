@@ -152,7 +152,7 @@ def run_ours(args, rank, world, local_rank):
                                       device=local_rank)
     sim.init(None)
     lib = sim._lib
-    engine = CudaSliceEngine(sim)  # also moves the simulation onto torch's current stream
+    engine = CudaSliceEngine(sim, p2p=(world > 1 and not args.nccl_allgather))  # also moves the simulation onto torch's current stream
     dsim = DistributedBarnesHutSimulation(engine, rank, world)
 
     def barrier():
@@ -228,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded %s, seed %d)" % (args.dist, args.seed),
-            "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)" % world,
+            "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)%s" % (world, "" if world == 1 else (", NCCL all-gather" if args.nccl_allgather else ", all-gather fused into the force kernel (peer stores over NVLink)")),
                        "l2": "working set (%.1f GB of tree + body state) is larger than the 126 MB L2; no flush needed" % (
                            (16 * (sim.numberOfNodes + 1) + 32 * n + 168 * (sim.numberOfNodes - n + 1) + 20 * n) / 1e9)},
             "clocks": clocks, "gpu_launches": launches,
@@ -287,6 +287,7 @@ def main():
     ap.add_argument("--dist", default="plummer", choices=["plummer", "uniform", "disks"])
     ap.add_argument("--seed", type=int, default=43)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-allgather", action="store_true", help="multi-GPU: NCCL all-gather instead of the peer-memory stores fused into the force kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -87,6 +87,9 @@ def load():
         "bh_calculate_force_slice": (C.c_int, [p, i32, i32]),
         "bh_apply_acceleration": (C.c_int, [p]),
         "bh_acc_sorted_device_ptr": (p, [p]),
+        "bh_ipc_export": (C.c_int, [p, p]),
+        "bh_ipc_set_peers": (C.c_int, [p, i32, i32, p]),
+        "bh_calculate_force_slice_p2p": (C.c_int, [p, i32, i32]),
         "bh_stage_async": (C.c_int, [p, i32]),
         "bh_read": (C.c_int, [p, i32, p, i64]),
         "bh_buffer_length": (i64, [p, i32]),

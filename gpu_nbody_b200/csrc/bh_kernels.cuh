@@ -541,11 +541,20 @@ __device__ __forceinline__ void force_accumulate(float2 dx, float2 dy, float2 dz
     az = __ffma2_rn(dz, f, az);
 }
 
+// Destinations of a slice's accelerations: the rank's own sorted-order buffer and, in a multi-GPU run with
+// peer memory, the same buffer of every other rank mapped over NVLink (CUDA IPC): the walk's epilogue stores
+// straight into all of them, so the all-gather is fused into the force kernel and overlaps the walk.
+constexpr int kMaxPeers = 16;
+struct PeerBuffers {
+    float4 *buf[kMaxPeers];
+    int count;
+};
+
 template <int VOTE, bool SLICE, bool COUNT>
 __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
                                                                  const int *__restrict__ oidx, const int *__restrict__ meta,
                                                                  const int *__restrict__ sorted, float4 *__restrict__ velacc,
-                                                                 float4 *__restrict__ accSorted, Scalars *sc, int n, int m,
+                                                                 const PeerBuffers dst, Scalars *sc, int n, int m,
                                                                  int first, int cnt, float thetaMacro, float eps, float dt) {
     __shared__ float dq[kMaxDepth];
     __shared__ int2 stack[kForce2Threads / 32][kStackCap];  // {cell - N, group bits | depth << 1}
@@ -688,7 +697,8 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         const int body = t ? b1 : b0;
         const float fx = t ? ax.y : ax.x, fy = t ? ay.y : ay.x, fz = t ? az.y : az.x;
         if (SLICE) {
-            accSorted[k0 + t] = make_float4(fx, fy, fz, 0.0f);
+            const float4 a = make_float4(fx, fy, fz, 0.0f);
+            for (int r = 0; r < dst.count; ++r) dst.buf[r][k0 + t] = a;  // own buffer, then the peers' (NVLink stores)
         } else {
             if (corr) {  // calculateforce.cl:174-179
                 float4 v = velacc[2 * (size_t)body];

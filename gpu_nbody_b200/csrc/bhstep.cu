@@ -49,6 +49,10 @@ struct Sim {
     double stageMs[BH_NUM_STAGES] = {};
     int64_t stageLaunches[BH_NUM_STAGES] = {};
     int64_t stepsTimed = 0;
+    // peer memory (multi-GPU): every rank's accSorted mapped through CUDA IPC; two phases (ping-pong per step)
+    int nranks = 1, rank = 0, accPhase = 0;
+    bool p2p = false;
+    float4 *peerAcc[bh::kMaxPeers] = {};
     std::string lastError;
 };
 
@@ -97,10 +101,19 @@ int resetState(Sim *s) {
     return BH_OK;
 }
 
+inline size_t accStride(const Sim *s) { return (size_t)s->n + kAccPad; }
+inline float4 *accPhase(const Sim *s) { return s->accSorted + (size_t)s->accPhase * accStride(s); }
+
 // force walk for sorted slots [first, first+cnt): fused velocity correction (slice = false) or
 // sorted-order acceleration output (slice = true)
-void launchForce(Sim *s, int first, int cnt, bool slice, bool counting) {
-#define BH_FORCE_ARGS2 s->node4, s->octet, s->oidx, s->meta, s->sorted, s->velacc, s->accSorted, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
+void launchForce(Sim *s, int first, int cnt, bool slice, bool counting, bool peers = false) {
+    bh::PeerBuffers dst;
+    dst.count = 1;
+    dst.buf[0] = accPhase(s);
+    if (peers)
+        for (int r = 0; r < s->nranks; ++r)
+            if (r != s->rank) dst.buf[dst.count++] = s->peerAcc[r] + (size_t)s->accPhase * accStride(s);
+#define BH_FORCE_ARGS2 s->node4, s->octet, s->oidx, s->meta, s->sorted, s->velacc, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
 #define BH_FORCE_DISPATCH(KERNEL, THREADS, BODIES, ARGS)                                                     \
     do {                                                                                                     \
         const int grid = (cnt + (BODIES) - 1) / (BODIES);                                                     \
@@ -277,7 +290,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     BH_ALLOC(s->node4, sizeof(float4) * ((size_t)m + 1));
     BH_ALLOC(s->velacc, sizeof(float4) * 2 * n);
     BH_ALLOC(s->octet, sizeof(float4) * 8 * nc);
-    BH_ALLOC(s->accSorted, sizeof(float4) * (n + kAccPad));
+    BH_ALLOC(s->accSorted, sizeof(float4) * 2 * (n + kAccPad));  // two phases, see bh_ipc_set_peers
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
@@ -305,7 +318,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     if ((e = cudaMemsetAsync(s->node4, 0, sizeof(float4) * ((size_t)m + 1), s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
     cudaMemsetAsync(s->velacc, 0, sizeof(float4) * 2 * n, s->stream);
     cudaMemsetAsync(s->sorted, 0, sizeof(int) * n, s->stream);
-    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * (n + kAccPad), s->stream);
+    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * 2 * (n + kAccPad), s->stream);
     if (resetState(s) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
         g_createError = s->lastError.empty() ? "initial reset failed" : s->lastError;
         bh_destroy(reinterpret_cast<bh_sim *>(s));
@@ -320,6 +333,8 @@ void bh_destroy(bh_sim *sim) {
     Sim *s = S(sim);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int r = 0; r < s->nranks; ++r)
+        if (s->p2p && r != s->rank && s->peerAcc[r]) cudaIpcCloseMemHandle(s->peerAcc[r]);
     cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
     cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta); cudaFree(s->oidx); cudaFree(s->parent); cudaFree(s->arrived);
     cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
@@ -461,13 +476,55 @@ int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
 
 int bh_apply_acceleration(bh_sim *sim) {
     BH_ENTER(sim);
-    bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->accSorted, s->sorted, s->velacc, s->sc, s->n, s->dt);
+    bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(accPhase(s), s->sorted, s->velacc, s->sc, s->n, s->dt);
     BH_CUDA(s, cudaGetLastError());
     s->stageLaunches[BH_STAGE_FORCE]++;
+    if (s->p2p) s->accPhase ^= 1;  // peers may already store the next step's slices while this kernel still reads
     return BH_OK;
 }
 
 void *bh_acc_sorted_device_ptr(bh_sim *sim) { return sim ? S(sim)->accSorted : nullptr; }
+
+int bh_ipc_export(bh_sim *sim, void *handle64) {
+    BH_ENTER(sim);
+    if (!handle64) return fail(s, BH_ERR_ARG, "handle64 is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    BH_CUDA(s, cudaIpcGetMemHandle(&h, s->accSorted));
+    memcpy(handle64, &h, sizeof h);
+    return BH_OK;
+}
+
+int bh_ipc_set_peers(bh_sim *sim, int32_t nranks, int32_t my_rank, const void *handles) {
+    BH_ENTER(sim);
+    if (nranks < 1 || nranks > bh::kMaxPeers || my_rank < 0 || my_rank >= nranks || !handles)
+        return fail(s, BH_ERR_ARG, "bad peer set (at most %d ranks)", bh::kMaxPeers);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == my_rank) { s->peerAcc[r] = s->accSorted; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + 64 * (size_t)r, sizeof h);
+        void *p = nullptr;
+        BH_CUDA(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peerAcc[r] = static_cast<float4 *>(p);
+    }
+    s->nranks = nranks;
+    s->rank = my_rank;
+    s->p2p = nranks > 1;
+    s->accPhase = 0;
+    return BH_OK;
+}
+
+int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count) {
+    BH_ENTER(sim);
+    if (!s->p2p) return fail(s, BH_ERR_ARG, "bh_ipc_set_peers has not been called");
+    if (first < 0 || count < 0 || (int64_t)first + count > s->n || (first % s->vote) != 0)
+        return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
+    if (count == 0) return BH_OK;
+    launchForce(s, first, count, true, false, true);
+    BH_CUDA(s, cudaGetLastError());
+    s->stageLaunches[BH_STAGE_FORCE]++;
+    return BH_OK;
+}
 
 int64_t bh_buffer_length(bh_sim *sim, int32_t which) {
     if (!sim) return BH_ERR_ARG;

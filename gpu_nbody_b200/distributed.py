@@ -9,7 +9,12 @@ this is the one natural shard of its step (DESIGN.md "Multi-GPU"):
   every rank   velocity correction + integrate for all bodies      (replicated, 68 B/body of HBM)
 
 Slices are equal-sized multiples of 32 sorted slots, so vote groups are exactly
-those of the single-GPU run and the all-gather is in place.  What crosses NVLink
+those of the single-GPU run and the all-gather is in place.  Two transports for
+the all-gather: NCCL (`all_gather_into_tensor`), or -- `p2p=True` -- fused into
+the force kernel: every rank's acceleration buffer is mapped into every other
+rank (CUDA IPC over NVLink) and the walk's epilogue stores each result straight
+into all of them, so the transfer overlaps the walk; one 1-element NCCL
+all-reduce on the stream is the cross-rank barrier before the buffer is read.  What crosses NVLink
 is 16 B per body per step (float4 acceleration); positions never travel because
 the integrate is replicated and bit-deterministic.
 
@@ -40,8 +45,9 @@ def slice_bounds(nbodies: int, world_size: int, align: int = SLICE_ALIGN):
 class CudaSliceEngine:
     """Adapter from GPUBarnesHutNBodySimulation to the slice contract of include/bhstep.h."""
 
-    def __init__(self, sim: GPUBarnesHutNBodySimulation):
+    def __init__(self, sim: GPUBarnesHutNBodySimulation, p2p: bool = False):
         import torch
+        self.p2p = p2p
         self.sim = sim
         self.lib = sim._lib
         self.h = sim.handle
@@ -66,8 +72,27 @@ class CudaSliceEngine:
         for st in range(4):  # bbox, build, summarise, sort
             self._rc(self.lib.bh_stage_async(self.h, st))
 
+    def connect_peers(self, rank, world_size, group=None):
+        """Exchange the CUDA IPC handles of the acceleration buffers (host side, once)."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        mine = C.create_string_buffer(64)
+        self._rc(self.lib.bh_ipc_export(self.h, mine))
+        handles = [None] * world_size
+        dist.all_gather_object(handles, mine.raw, group=group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * world_size)
+        self._rc(self.lib.bh_ipc_set_peers(self.h, world_size, rank, blob))
+        self._flag = torch.zeros(1, device=self.device)
+        self._group = group
+
     def force_slice(self, first, count):
-        self._rc(self.lib.bh_calculate_force_slice(self.h, first, count))
+        if self.p2p:
+            import torch.distributed as dist
+            self._rc(self.lib.bh_calculate_force_slice_p2p(self.h, first, count))
+            dist.all_reduce(self._flag, group=self._group)  # stream-ordered barrier: every rank's stores have landed
+        else:
+            self._rc(self.lib.bh_calculate_force_slice(self.h, first, count))
 
     def apply_and_integrate(self):
         self._rc(self.lib.bh_apply_acceleration(self.h))
@@ -85,6 +110,9 @@ class DistributedBarnesHutSimulation:
         self.chunk, self.bounds = slice_bounds(engine.nbodies, world_size)
         if self.chunk * world_size > engine.acc_sorted.shape[0]:
             raise ValueError("acceleration buffer too small for %d ranks" % world_size)
+        self.fused = bool(getattr(engine, "p2p", False)) and world_size > 1
+        if self.fused:
+            engine.connect_peers(rank, world_size, group)
 
     def step_async(self, nsteps: int = 1):
         import torch.distributed as dist
@@ -94,7 +122,7 @@ class DistributedBarnesHutSimulation:
         for _ in range(nsteps):
             self.engine.tree_stages()
             self.engine.force_slice(first, count)
-            if self.world_size > 1:
+            if self.world_size > 1 and not self.fused:
                 dist.all_gather_into_tensor(full, mine, group=self.group)
             self.engine.apply_and_integrate()
 

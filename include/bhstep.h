@@ -132,6 +132,15 @@ int bh_check(bh_sim *sim); /* sync + error buffer */
 int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count);
 int bh_apply_acceleration(bh_sim *sim);
 void *bh_acc_sorted_device_ptr(bh_sim *sim); /* float4[N + 2048] in device memory (slack for equal, aligned slices) */
+/* Peer-memory variant (one process per GPU, one node): the all-gather is fused into the force kernel.
+ * Every rank exports its acceleration buffer (bh_ipc_export: 64-byte CUDA IPC handle), the host exchanges
+ * the handles (any transport) and hands all of them to bh_ipc_set_peers; bh_calculate_force_slice_p2p then
+ * stores each slot's result into the own buffer and, over NVLink, into every peer's.  The caller must put
+ * one cross-rank barrier on the stream (e.g. a 1-element NCCL all-reduce) between this call and
+ * bh_apply_acceleration; the buffer is double-buffered per step, so no second barrier is needed. */
+int bh_ipc_export(bh_sim *sim, void *handle64);
+int bh_ipc_set_peers(bh_sim *sim, int32_t nranks, int32_t my_rank, const void *handles /* nranks x 64 bytes */);
+int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count);
 /* Async single stages for callers that sequence their own stream. */
 int bh_stage_async(bh_sim *sim, int32_t stage /* enum bh_stage */);
 

@@ -23,7 +23,7 @@ n, steps = %(n)d, %(steps)d
 arrays = U.generate_arrays(U.PlummerUniverseGenerator(123), n)
 sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.ArrayUniverseGenerator(*arrays), device=local)
 sim.init(None)
-dsim = DistributedBarnesHutSimulation(CudaSliceEngine(sim), rank, world)
+dsim = DistributedBarnesHutSimulation(CudaSliceEngine(sim, p2p=%(p2p)s), rank, world)
 dsim.step(steps)
 np.savez(os.path.join(%(out)r, "rank%%d.npz" %% rank), **{k: sim.readBuffer(k, n) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "accY", "accZ", "sorted")})
 dist.barrier()
@@ -31,15 +31,16 @@ dist.destroy_process_group()
 '''
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("n", [100000, 4097])
-def test_ranks_equal_single_gpu(tmp_path, n):
+def test_ranks_equal_single_gpu(tmp_path, n, p2p):
     import torch
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     steps = 3
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT, "n": n, "steps": steps, "out": str(tmp_path)})
+    script.write_text(WORKER % {"root": ROOT, "n": n, "steps": steps, "out": str(tmp_path), "p2p": p2p})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + os.getpid() % 200), str(script)]
     subprocess.run(cmd, check=True, timeout=600)
