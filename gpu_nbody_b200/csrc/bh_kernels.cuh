@@ -638,46 +638,69 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         const float mscale = mine ? 1.0f : 0.0f;
         const int ncell = mt & 15, nbody = mt >> 4;
         __syncwarp();
-#define BH_DIST(c)                                                                                                     \
-    const float2 dx = __fadd2_rn(make_float2((c).x, (c).x), npx); /* c - p, exactly */                                 \
-    const float2 dy = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                      \
-    const float2 dz = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                      \
-    const float2 r2 = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), eps2); /* :138-143 */
+#define BH_DIST(c, S)                                                                                                  \
+    const float2 dx##S = __fadd2_rn(make_float2((c).x, (c).x), npx); /* c - p, exactly */                              \
+    const float2 dy##S = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                   \
+    const float2 dz##S = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                   \
+    const float2 r2##S = __fadd2_rn(__ffma2_rn(dz##S, dz##S, __ffma2_rn(dy##S, dy##S, __fmul2_rn(dx##S, dx##S))), eps2); /* :138-143 */
+        // one child cell whose vote was not unanimous (or that was not tested as part of a pair)
+#define BH_CELL_VOTE(c, S, far, j)                                                                                     \
+    if (__all_sync(kFull, far)) { /* far enough for every body of the warp: every group that is here uses it */      \
+        force_accumulate(dx##S, dy##S, dz##S, r2##S, __fmul_rn((c).w, mscale), ax, ay, az);                            \
+        if (COUNT && mine) nInter += nact;                                                                             \
+    } else {                                                                                                           \
+        const unsigned near = __ballot_sync(kFull, !(far));                                                            \
+        const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                             \
+        if (open) { /* :154-163 */                                                                                     \
+            const int ch = lds_s32(rowBase + 128u + 4u * (j));                                                         \
+            sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));                                                 \
+            sp += 8;                                                                                                   \
+            if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));                                        \
+        }                                                                                                              \
+        if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                             \
+        if (bits & ~open) { /* at least one group uses the cell as a point mass */                                    \
+            const bool use = mine && (near & gm) == 0u;                                                                \
+            force_accumulate(dx##S, dy##S, dz##S, r2##S, use ? (c).w : 0.0f, ax, ay, az);                              \
+            if (COUNT && use) nInter += nact;                                                                          \
+        }                                                                                                              \
+    }
+        // Child cells come first and are taken two at a time: two independent distance chains per lane hide the
+        // fp32 latency (dependency waits were the top stall), and the common case -- both cells far from every
+        // body of the warp (the group vote of :145 is then unanimous in all groups) -- costs one VOTE for two.
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // child cells come first
-            if (j >= ncell) break;
-            const float4 c = lds_v4(rowBase + 16u * j);
-            BH_DIST(c)
-            const bool far = r2.x >= thr && r2.y >= thr;  // the group votes, :145
-            if (__all_sync(kFull, far)) {  // far enough for every body of the warp: every group that is here uses it
-                force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);
-                if (COUNT && mine) nInter += nact;
+        for (int j = 0; j < 8; j += 2) {
+            if (j + 2 > ncell) break;
+            const float4 c0 = lds_v4(rowBase + 16u * j), c1 = lds_v4(rowBase + 16u * (j + 1));
+            BH_DIST(c0, 0)
+            BH_DIST(c1, 1)
+            const bool far0 = r20.x >= thr && r20.y >= thr, far1 = r21.x >= thr && r21.y >= thr;
+            if (__all_sync(kFull, far0 && far1)) {
+                const float mw0 = __fmul_rn(c0.w, mscale), mw1 = __fmul_rn(c1.w, mscale);
+                force_accumulate(dx0, dy0, dz0, r20, mw0, ax, ay, az);
+                force_accumulate(dx1, dy1, dz1, r21, mw1, ax, ay, az);
+                if (COUNT && mine) nInter += 2 * nact;
             } else {
-                const unsigned near = __ballot_sync(kFull, !far);
-                const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);
-                if (open) {  // :154-163
-                    const int ch = lds_s32(rowBase + 128u + 4u * j);
-                    sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));
-                    sp += 8;
-                    if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));
-                }
-                if (COUNT && (near & gmMine) != 0u) nOpen += nact;
-                if (bits & ~open) {  // at least one group uses the cell as a point mass
-                    const bool use = mine && (near & gm) == 0u;
-                    force_accumulate(dx, dy, dz, r2, use ? c.w : 0.0f, ax, ay, az);
-                    if (COUNT && use) nInter += nact;
-                }
+                BH_CELL_VOTE(c0, 0, far0, j)
+                BH_CELL_VOTE(c1, 1, far1, j + 1)
             }
+        }
+        if (ncell & 1) {  // the odd one
+            const int j = ncell - 1;
+            const float4 c0 = lds_v4(rowBase + 16u * (unsigned)j);
+            BH_DIST(c0, 0)
+            const bool far0 = r20.x >= thr && r20.y >= thr;
+            BH_CELL_VOTE(c0, 0, far0, j)
         }
         const unsigned brow = rowBase + 16u * (unsigned)ncell;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // then child bodies: always used (:145 child < NBODIES)
             if (j >= nbody) break;
-            const float4 c = lds_v4(brow + 16u * j);
-            BH_DIST(c)
-            force_accumulate(dx, dy, dz, r2, __fmul_rn(c.w, mscale), ax, ay, az);
+            const float4 c0 = lds_v4(brow + 16u * j);
+            BH_DIST(c0, 0)
+            force_accumulate(dx0, dy0, dz0, r20, __fmul_rn(c0.w, mscale), ax, ay, az);
             if (COUNT && mine) nInter += nact;
         }
+#undef BH_CELL_VOTE
 #undef BH_DIST
     }
     if (COUNT) {
