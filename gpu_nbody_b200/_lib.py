@@ -26,6 +26,10 @@ FLOAT_BUFFERS = {"posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "accY",
 STAGES = ["bounding_box", "build_tree", "summarize", "sort", "calculate_force", "integrate"]
 
 
+class BhDiag(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("ekin", "epot", "px", "py", "pz", "mass")]
+
+
 class BhStats(C.Structure):
     _fields_ = [("nbodies", C.c_int32), ("number_of_nodes", C.c_int32), ("cells_used", C.c_int32),
                 ("max_depth", C.c_int32), ("step", C.c_int32), ("error", C.c_int32),
@@ -95,6 +99,9 @@ def load():
         "bh_buffer_length": (i64, [p, i32]),
         "bh_copy_vertices": (C.c_int, [p, p, p]),
         "bh_stats": (C.c_int, [p, C.POINTER(BhStats)]),
+        "bh_diagnostics": (C.c_int, [p, i32, C.POINTER(BhDiag)]),
+        "bh_universe_file_bodies": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
+        "bh_upload_universe_file": (C.c_int, [p, C.c_char_p]),
         "bh_reset_stats": (C.c_int, [p]),
         "bh_number_of_bodies": (i32, [p]),
         "bh_number_of_nodes": (i32, [i32]),

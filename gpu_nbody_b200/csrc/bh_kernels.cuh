@@ -833,6 +833,58 @@ __global__ void copy_vertices_kernel(const float4 *__restrict__ node4, const flo
     }
 }
 
+// ---- diagnostics (GPUBH:305-365 printEnergy / printImpulse, on the device) ---------------------------
+// out[0] = sum 1/2 m v^2, out[1..3] = sum m v, out[4] = sum m; double accumulation.
+__global__ void __launch_bounds__(256) kinetic_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ velacc,
+                                                      double *__restrict__ out, int n) {
+    double e = 0.0, px = 0.0, py = 0.0, pz = 0.0, ms = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float m = node4[i].w;
+        const float4 v = velacc[2 * (size_t)i];
+        e += 0.5 * m * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z);
+        px += (double)m * v.x; py += (double)m * v.y; pz += (double)m * v.z; ms += m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o); px += __shfl_xor_sync(0xffffffffu, px, o);
+        py += __shfl_xor_sync(0xffffffffu, py, o); pz += __shfl_xor_sync(0xffffffffu, pz, o);
+        ms += __shfl_xor_sync(0xffffffffu, ms, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 0, e); atomicAdd(out + 1, px); atomicAdd(out + 2, py); atomicAdd(out + 3, pz); atomicAdd(out + 4, ms);
+    }
+}
+
+// out[5] += -1/2 sum_i m_i sum_{j != i} m_j / sqrt(r_ij^2 + eps): the softened potential of the parity tests
+// (not the reference's unsoftened, doubled printEnergy term).  Direct sum, j-tiles staged through shared memory,
+// fp32 pair terms, per-tile fp32 partial sums folded into double.
+constexpr int kPotTile = 256;
+__global__ void __launch_bounds__(kPotTile) potential_kernel(const float4 *__restrict__ node4, double *__restrict__ out, int n,
+                                                             float eps) {
+    __shared__ float4 tile[kPotTile];
+    const int i = blockIdx.x * kPotTile + threadIdx.x;
+    const float4 pi = node4[min(i, n - 1)];
+    double phi = 0.0;
+    for (int j0 = 0; j0 < n; j0 += kPotTile) {
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = j < n ? node4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        float part = 0.0f;
+#pragma unroll 8
+        for (int t = 0; t < kPotTile; ++t) {
+            const float4 pj = tile[t];
+            const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) + eps;
+            const float w = (j0 + t == i) ? 0.0f : pj.w;  // no self term; padded slots have mass 0
+            part = fmaf(w, rsqrtf(r2), part);
+        }
+        phi += part;
+        __syncthreads();
+    }
+    double e = i < n ? -0.5 * (double)pi.w * phi : 0.0;
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + 5, e);
+}
+
 // ---- measurement utility: FP32 FMA peak of the device (roofline denominator of the force kernel) ----
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;

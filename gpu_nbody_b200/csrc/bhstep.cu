@@ -646,6 +646,86 @@ int bh_reset_stats(bh_sim *sim) {
 
 int32_t bh_number_of_bodies(bh_sim *sim) { return sim ? S(sim)->n : BH_ERR_ARG; }
 
+int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
+    BH_ENTER(sim);
+    if (!out) return fail(s, BH_ERR_ARG, "out is NULL");
+    int rc = ensureStaging(s, 8 * sizeof(double));
+    if (rc) return rc;
+    double *d = static_cast<double *>(s->staging);
+    BH_CUDA(s, cudaMemsetAsync(d, 0, 8 * sizeof(double), s->stream));
+    bh::kinetic_kernel<<<std::min((s->n + 255) / 256, s->numSMs * 8), 256, 0, s->stream>>>(s->node4, s->velacc, d, s->n);
+    if (with_potential)
+        bh::potential_kernel<<<(s->n + bh::kPotTile - 1) / bh::kPotTile, bh::kPotTile, 0, s->stream>>>(s->node4, d, s->n, s->eps);
+    BH_CUDA(s, cudaGetLastError());
+    double h[8];
+    BH_CUDA(s, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    out->ekin = h[0]; out->px = h[1]; out->py = h[2]; out->pz = h[3]; out->mass = h[4];
+    out->epot = with_potential ? h[5] : 0.0;
+    return BH_OK;
+}
+
+// ---- .universe files (Java ObjectOutputStream layout, UniverseSerializer.java:25-34) ----
+namespace {
+struct UniverseFile {
+    int32_t n = 0;
+    std::string error;
+    float *arrays[7] = {};
+    ~UniverseFile() { for (auto *a : arrays) free(a); }
+};
+uint32_t be32(const unsigned char *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+bool readUniverse(const char *path, bool headerOnly, UniverseFile &u) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { u.error = std::string("cannot open ") + path; return false; }
+    unsigned char hdr[10];
+    static const unsigned char magic[6] = {0xAC, 0xED, 0x00, 0x05, 0x77, 0x04};  // stream header + TC_BLOCKDATA(4) = writeInt
+    if (fread(hdr, 1, 10, f) != 10 || memcmp(hdr, magic, 6) != 0) { fclose(f); u.error = "not a .universe file (Java stream with a leading writeInt expected)"; return false; }
+    u.n = (int32_t)be32(hdr + 6);
+    if (headerOnly) { fclose(f); return true; }
+    static const unsigned char classDesc[] = {0x72, 0x00, 0x02, '[', 'F', 0x0B, 0x9C, 0x81, 0x89, 0x22, 0xE0, 0x0C, 0x42, 0x02, 0x00, 0x00, 0x78, 0x70};
+    static const unsigned char classRef[] = {0x71, 0x00, 0x7E, 0x00, 0x00};
+    for (int a = 0; a < 7; ++a) {
+        unsigned char tag[32];
+        if (fread(tag, 1, 2, f) != 2 || tag[0] != 0x75) { fclose(f); u.error = "expected TC_ARRAY"; return false; }
+        const bool full = tag[1] == 0x72;
+        const size_t rest = (full ? sizeof classDesc : sizeof classRef) - 1;
+        if (fread(tag + 2, 1, rest, f) != rest || memcmp(tag + 1, full ? classDesc : classRef, rest + 1) != 0) {
+            fclose(f); u.error = "unexpected array class (float[] expected)"; return false;
+        }
+        unsigned char len[4];
+        if (fread(len, 1, 4, f) != 4 || (int32_t)be32(len) != u.n) { fclose(f); u.error = "array length differs from nbodies"; return false; }
+        u.arrays[a] = static_cast<float *>(malloc(sizeof(float) * (size_t)std::max(u.n, 1)));
+        std::string buf(4 * (size_t)u.n, '\0');
+        if (!u.arrays[a] || fread(&buf[0], 1, buf.size(), f) != buf.size()) { fclose(f); u.error = "short read"; return false; }
+        for (int32_t i = 0; i < u.n; ++i) {
+            const uint32_t v = be32(reinterpret_cast<const unsigned char *>(buf.data()) + 4 * (size_t)i);
+            memcpy(&u.arrays[a][i], &v, 4);
+        }
+    }
+    fclose(f);
+    return true;
+}
+}  // namespace
+
+int bh_universe_file_bodies(const char *path, int32_t *nbodies) {
+    if (!path || !nbodies) return BH_ERR_ARG;
+    UniverseFile u;
+    if (!readUniverse(path, true, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
+    *nbodies = u.n;
+    return BH_OK;
+}
+
+int bh_upload_universe_file(bh_sim *sim, const char *path) {
+    BH_ENTER(sim);
+    if (!path) return fail(s, BH_ERR_ARG, "path is NULL");
+    UniverseFile u;
+    if (!readUniverse(path, false, u)) return fail(s, BH_ERR_ARG, "%s", u.error.c_str());
+    if (u.n != s->n)  // SerializedUniverseGenerator.java:41-42 IllegalStateException
+        return fail(s, BH_ERR_ARG, "invalid amount of bodies for serialized universe (%d in the file, %d in the simulation)", u.n, s->n);
+    const float *src[7] = {u.arrays[0], u.arrays[1], u.arrays[2], u.arrays[3], u.arrays[4], u.arrays[5], u.arrays[6]};
+    return uploadImpl(s, src, cudaMemcpyHostToDevice);
+}
+
 int bh_measure_fp32_peak(int32_t device, double *tflops) {
     if (!tflops) return BH_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, BH_ERR_CUDA, "cudaSetDevice(%d) failed", device);

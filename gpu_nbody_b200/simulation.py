@@ -163,6 +163,18 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
     def setStream(self, cuda_stream): self._check(self._lib.bh_set_stream(self._sim, C.c_void_p(cuda_stream)))
     def resetStats(self): self._check(self._lib.bh_reset_stats(self._sim))
 
+    def diagnostics(self, with_potential=True):
+        """printEnergy / printImpulse (GPUBH:305-365) on the device: dict(ekin, epot, etot, px, py, pz, mass)."""
+        d = _lib.BhDiag()
+        self._check(self._lib.bh_diagnostics(self._sim, int(with_potential), C.byref(d)))
+        out = {k: getattr(d, k) for k, _ in d._fields_}
+        out["etot"] = out["ekin"] + out["epot"]
+        return out
+
+    def uploadUniverseFile(self, path):
+        """SerializedUniverseGenerator without a JVM: read a .universe file natively and upload it."""
+        self._check(self._lib.bh_upload_universe_file(self._sim, str(path).encode()))
+
     def stats(self):
         st = _lib.BhStats()
         self._check(self._lib.bh_stats(self._sim, C.byref(st)))

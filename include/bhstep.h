@@ -154,6 +154,19 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which);
  * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
 int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
 
+/* printEnergy / printImpulse (GPUBH:305-365) as device reductions instead of O(N^2) host loops:
+ * kinetic energy, momentum, total mass, and -- if with_potential -- the softened potential
+ * -sum_{i<j} m_i m_j / sqrt(r^2 + eps2) by a tiled direct sum (the parity tests' energy formula; the
+ * reference's own printEnergy uses an unsoftened, doubled potential and is not reproduced). */
+typedef struct bh_diag_t { double ekin, epot, px, py, pz, mass; } bh_diag_t;
+int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out);
+
+/* SerializedUniverseGenerator (universe/serialize/SerializedUniverseGenerator.java:21-53) without a JVM:
+ * reads a .universe file (Java ObjectOutputStream layout of UniverseSerializer.java:25-34) and uploads it;
+ * fails like the reference when the body count differs from the simulation's. */
+int bh_universe_file_bodies(const char *path, int32_t *nbodies);
+int bh_upload_universe_file(bh_sim *sim, const char *path);
+
 int bh_stats(bh_sim *sim, bh_stats_t *out);
 int bh_reset_stats(bh_sim *sim);
 int32_t bh_number_of_bodies(bh_sim *sim);          /* getNumberOfBodies(), GPUBH:377-379 */

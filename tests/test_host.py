@@ -100,3 +100,16 @@ def test_slice_bounds():
         assert sum(c for _, c in b) == n and all(f % 32 == 0 for f, _ in b)
         nonempty = [(f, c) for f, c in b if c]
         assert nonempty[0][0] == 0 and all(nonempty[i][0] == nonempty[i - 1][0] + nonempty[i - 1][1] for i in range(1, len(nonempty)))
+
+
+def test_native_universe_reader_header(tmp_path):
+    """bh_universe_file_bodies parses the Java stream header written by write_universe (no GPU needed)."""
+    lib = _lib.load()
+    arrs = U.generate_arrays(U.PlummerUniverseGenerator(3), 77)
+    p = tmp_path / "u.universe"
+    U.write_universe(p, *arrs)
+    n = C.c_int32()
+    assert lib.bh_universe_file_bodies(str(p).encode(), C.byref(n)) == 0 and n.value == 77
+    bad = tmp_path / "bad.universe"
+    bad.write_bytes(b"\xac\xed\x00\x05\x73\x72" + b"\0" * 64)  # the legacy layout (writeObject(Integer) first)
+    assert lib.bh_universe_file_bodies(str(bad).encode(), C.byref(n)) == -2

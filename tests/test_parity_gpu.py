@@ -202,3 +202,42 @@ def test_full_size_properties_1m():
     err = np.linalg.norm(acc[:512] - d, axis=1) / np.linalg.norm(d, axis=1)
     assert np.median(err) < 5e-3
     sim.close()
+
+
+def test_device_diagnostics_match_host_energy():
+    """bh_diagnostics (printEnergy / printImpulse on the device) against the oracle's double-precision O(N^2) sum."""
+    import oracle
+    n = 20000
+    a = gen(U.PlummerUniverseGenerator(8), n)
+    sim, _ = parity.make_pair(a, counting=False)
+    sim.step(5)
+    d = sim.diagnostics()
+    g = [sim.readBuffer(k, n) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "mass")]
+    ek, ep = oracle.energy(*g)
+    assert abs(d["ekin"] - ek) <= 1e-9 * abs(ek)
+    assert abs(d["epot"] - ep) <= 2e-6 * abs(ep)
+    m = g[6].astype(np.float64)
+    for k, v in zip(("px", "py", "pz"), g[3:6]):
+        assert abs(d[k] - float((m * v).sum())) < 1e-9
+    assert abs(d["mass"] - float(m.sum())) < 1e-12
+    sim.close()
+
+
+def test_native_universe_file_upload(tmp_path):
+    """bh_upload_universe_file == SerializedUniverseGenerator + loadBuffers, including the size check."""
+    n = 3000
+    a = gen(U.PlummerUniverseGenerator(4), n)
+    path = tmp_path / "p.universe"
+    U.write_universe(path, *a)
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.RandomCubicUniverseGenerator(6.0, 1))
+    sim.init(None)
+    sim.uploadUniverseFile(path)
+    for k, src in zip(("posX", "posY", "posZ", "velX", "velY", "velZ", "mass"), a):
+        assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), src.view(np.uint32))
+    assert sim.scalar("step") == -1
+    sim.close()
+    other = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n + 16, U.RandomCubicUniverseGenerator(6.0, 1))
+    other.init(None)
+    with pytest.raises(BhError):  # SerializedUniverseGenerator.java:41-42
+        other.uploadUniverseFile(path)
+    other.close()
