@@ -146,11 +146,32 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.bodies, args.steps, max(3, args.warmup)
-    arrays = make_universe(args.dist, n, args.seed)
-
-    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.ArrayUniverseGenerator(*arrays), theta=THETA, eps2=EPS2, dt=DT, vote_width=16,
-                                      device=local_rank)
-    sim.init(None)
+    if args.gpu_gen:
+        # memory-sized configurations (BASELINE configs[3], 10^8 bodies): the universe is drawn on the device
+        # (torch CUDA generator, same seed on every rank = same bytes) and handed over with bh_upload_device
+        if args.dist != "uniform":
+            raise SystemExit("--gpu-gen supports --dist uniform (RandomCubicUniverseGenerator(6): (U-0.5)*6 per axis, v = 0, m = 1/n)")
+        g = torch.Generator(device=dev); g.manual_seed(args.seed)
+        dev_arrays = [((torch.rand(n, device=dev, generator=g) - 0.5) * 6.0).contiguous() for _ in range(3)]
+        dev_arrays += [torch.zeros(n, device=dev) for _ in range(3)] + [torch.full((n,), 1.0 / n, device=dev)]
+        arrays = None
+        sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.RandomCubicUniverseGenerator(6.0, args.seed), theta=THETA, eps2=EPS2, dt=DT,
+                                          vote_width=16, device=local_rank)
+        sim._lib = _lib.load()
+        import ctypes as C
+        rc = sim._lib.bh_create(C.byref(sim._sim), n, THETA, EPS2, DT, 16, local_rank)
+        if rc != 0:
+            raise SystemExit("bh_create failed: %r" % sim._lib.bh_last_error(None))
+        sim.numberOfNodes = int(sim._lib.bh_number_of_nodes(n))
+        torch.cuda.synchronize()
+        sim._check(sim._lib.bh_upload_device(sim.handle, *(t.data_ptr() for t in dev_arrays)))
+        del dev_arrays
+        torch.cuda.empty_cache()
+    else:
+        arrays = make_universe(args.dist, n, args.seed)
+        sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.ArrayUniverseGenerator(*arrays), theta=THETA, eps2=EPS2, dt=DT, vote_width=16,
+                                          device=local_rank)
+        sim.init(None)
     lib = sim._lib
     engine = CudaSliceEngine(sim, p2p=(world > 1 and not args.nccl_allgather))  # also moves the simulation onto torch's current stream
     dsim = DistributedBarnesHutSimulation(engine, rank, world)
@@ -194,6 +215,18 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = {k: (v / st["steps_timed"] if st["steps_timed"] else None) for k, v in st["stage_ms"].items()}
 
     # ---- e2e: host buffers in, host buffers out, every step ----
+    if args.gpu_gen:
+        if rank == 0:
+            value = n * K / (ms_total * 1e-3)
+            print(json.dumps({"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                              "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic (uniform cube drawn on the device, torch CUDA generator seed %d)" % args.seed,
+                              "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)" % world},
+                              "clocks": clocks, "gpu_launches": launches, "e2e": None, "cells_used": st["cells_used"], "max_depth": st["max_depth"],
+                              "stage_ms": stage_ms}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in arrays]
     pos4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
     vel4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
@@ -287,6 +320,7 @@ def main():
     ap.add_argument("--dist", default="plummer", choices=["plummer", "uniform", "disks"])
     ap.add_argument("--seed", type=int, default=43)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gpu-gen", action="store_true", help="draw the universe on the device (memory-sized runs; skips the e2e and cpu legs)")
     ap.add_argument("--nccl-allgather", action="store_true", help="multi-GPU: NCCL all-gather instead of the peer-memory stores fused into the force kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
