@@ -261,7 +261,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded %s, seed %d)" % (args.dist, args.seed),
-            "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)%s" % (world, "" if world == 1 else (", NCCL all-gather" if args.nccl_allgather else ", all-gather fused into the force kernel (peer stores over NVLink)")),
+            "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)%s" % (world, "" if world == 1 else (", all-gather fused into the force kernel (peer stores over NVLink)" if dsim.fused else ", NCCL all-gather")),
                        "l2": "working set (%.1f GB of tree + body state) is larger than the 126 MB L2; no flush needed" % (
                            (16 * (sim.numberOfNodes + 1) + 32 * n + 168 * (sim.numberOfNodes - n + 1) + 20 * n) / 1e9)},
             "clocks": clocks, "gpu_launches": launches,

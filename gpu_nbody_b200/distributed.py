@@ -112,7 +112,19 @@ class DistributedBarnesHutSimulation:
             raise ValueError("acceleration buffer too small for %d ranks" % world_size)
         self.fused = bool(getattr(engine, "p2p", False)) and world_size > 1
         if self.fused:
-            engine.connect_peers(rank, world_size, group)
+            # every rank must take the same path: agree on whether peer mapping worked everywhere
+            import torch
+            import torch.distributed as dist
+            try:
+                engine.connect_peers(rank, world_size, group)
+                ok = 1
+            except Exception as exc:  # no peer access between some pair of devices: use the NCCL all-gather
+                self.peer_error = str(exc)
+                ok = 0
+            flag = torch.tensor([ok], device=engine.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            self.fused = bool(flag.item())
+            engine.p2p = self.fused
 
     def step_async(self, nsteps: int = 1):
         import torch.distributed as dist
