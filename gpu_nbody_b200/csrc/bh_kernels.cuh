@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                     busy = false;
                 } else {
                     const int patch = cell;
+                    const int node0 = node;  // the cell whose leaf slot is being split
                     int cur = node, curPath = path;
                     for (;;) {
                         ++depth;
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                         start[cell - n] = -1;
                         count[cell - n] = -1;
                         parent[cell - n] = cur;  // for the counter-driven summarise
-                        arrived[cell - n] = 0;
                         const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
                         const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
+                        arrived[cell - n] = (qPath == pPath) ? (1 << 16) : 0;  // (#child cells << 16) | reports received
                         int *row = child + (size_t)(cell - n) * 8;
                         const int4 empty = make_int4(-1, -1, -1, -1);
                         reinterpret_cast<int4 *>(row)[0] = empty;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                     pathLen = min(depth, kPathCap);
                     node = cur;
                     path = curPath;
+                    atomicAdd(arrived + (node0 - n), 1 << 16);  // the leaf's cell gains a child cell
                     __threadfence();          // :173 publish the sub-tree ...
                     st_relaxed(slot, patch);  // :180 ... by replacing the lock
                     localMaxDepth = max(localMaxDepth, depth);
@@ -346,16 +348,12 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
 // order and spins on children that are not ready; on 10^7 bodies most threads
 // then sit in long parent-child chains.  Here the pass is counter driven and
 // never waits: every cell collects one report per child cell plus one from its
-// own thread (`arrived`, reset at creation); whoever reports last summarises the
-// cell, reports to the parent and climbs on.  Children are summed in octant order,
+// own thread (`arrived`: build keeps the number of child cells in the high half,
+// reports count up in the low half; a small array that stays in L2); whoever
+// reports last summarises the cell, reports to the parent and climbs on.  Children are summed in octant order,
 // which makes the result independent of timing and bit-identical to the oracle.
 // The summarising thread also writes the force walk's record of the cell.
 constexpr int kSummThreads = 256;
-
-__device__ __forceinline__ int count_child_cells(const int *row, int n) {
-    const int4 lo = __ldcg(reinterpret_cast<const int4 *>(row)), hi = __ldcg(reinterpret_cast<const int4 *>(row) + 1);
-    return (lo.x >= n) + (lo.y >= n) + (lo.z >= n) + (lo.w >= n) + (hi.x >= n) + (hi.y >= n) + (hi.z >= n) + (hi.w >= n);
-}
 
 __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
                                                                  float4 *__restrict__ octet, int *__restrict__ oidx,
@@ -370,9 +368,11 @@ __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__re
     const int stride = gridDim.x * blockDim.x;
     for (int first = bottom + blockIdx.x * blockDim.x + threadIdx.x; first <= m; first += stride) {
         int cell = first;
-        // a cell is summarised by whoever arrives last among its child cells and its own thread; its row stays
-        // untouched until then, so counting the child cells here cannot race with the compaction below
-        if (atomicAdd(arrived + (cell - n), 1) != count_child_cells(child + (size_t)(cell - n) * 8, n)) continue;
+        // A cell is summarised by whoever reports last among its child cells and its own thread.  `arrived` holds
+        // the number of child cells (maintained by build) in its high half and the reports in its low half, so one
+        // atomic on a small, L2-resident array both reports and tells whether this was the last report.
+        int old = atomicAdd(arrived + (cell - n), 1);
+        if ((old & 0xffff) != (old >> 16)) continue;
         __threadfence();
         for (;;) {
             int *row = child + (size_t)(cell - n) * 8;
@@ -435,9 +435,9 @@ __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__re
             if (cell == m) break;                // the root
             // report to the parent; the child that reports last continues with it
             const int par = parent[cell - n];
-            const int need = count_child_cells(child + (size_t)(par - n) * 8, n);
             __threadfence();  // summarizetree.cl:170: this cell's record before the report
-            if (atomicAdd(arrived + (par - n), 1) != need) break;  // need child cells + the parent's own thread
+            old = atomicAdd(arrived + (par - n), 1);
+            if ((old & 0xffff) != (old >> 16)) break;  // not the last report: somebody else continues
             __threadfence();
             cell = par;
         }
