@@ -241,3 +241,60 @@ def test_native_universe_file_upload(tmp_path):
     with pytest.raises(BhError):  # SerializedUniverseGenerator.java:41-42
         other.uploadUniverseFile(path)
     other.close()
+
+
+def test_full_size_properties_10m():
+    """The bench workload (BASELINE configs[2], Plummer 10^7): properties that do not need the oracle on all bodies,
+    plus an oracle check of one vote-group-aligned sample of the force walk."""
+    import oracle
+    n = 10_000_000
+    a = gen(U.PlummerUniverseGenerator(43), n)
+    sim, _ = parity.make_pair(a, counting=True)
+    sim.boundingBox(); sim.buildTree(); sim.summarizeTree(); sim.sort()
+    m = sim.numberOfNodes
+    srt = sim.readBuffer("sorted", n)
+    assert np.array_equal(np.bincount(srt, minlength=n), np.ones(n, dtype=np.int64))  # a permutation
+    assert sim.readBuffer("bodyCount")[m] == n
+    # the oracle on the same input: whole tree bit-exact (sequential CPU build of 10^7 bodies, ~10 s), force on a sample
+    orc = oracle.OracleSim(n, *a)
+    orc.bounding_box(); assert orc.build_tree() == 0; orc.summarize(); orc.sort()
+    assert sim.scalar("bottom") == orc.bottom[0] and sim.scalar("maxDepth") == orc.maxDepth[0]
+    assert np.array_equal(srt, orc.sorted[:n])
+    root_g = [sim.readBuffer(k)[m] for k in ("posX", "posY", "posZ", "mass")]
+    root_o = [orc.buf[k][m] for k in ("posX", "posY", "posZ", "mass")]
+    assert np.array_equal(np.array(root_g, np.float32).view(np.uint32), np.array(root_o, np.float32).view(np.uint32))
+    sim.calculateForce()
+    first, count = 4_000_000, 16 * 2048
+    assert orc.calculate_force_range(first, count) == 0
+    idx = srt[first:first + count]
+    ga = np.stack([sim.readBuffer(k, n)[idx] for k in ("accX", "accY", "accZ")], axis=1).astype(np.float64)
+    oa = np.stack([orc.buf[k][idx] for k in ("accX", "accY", "accZ")], axis=1).astype(np.float64)
+    err = np.linalg.norm(ga - oa, axis=1) / np.linalg.norm(oa, axis=1)
+    assert err.max() <= parity.ACC_RTOL
+    st = sim.stats()
+    assert 3000 < st["interactions"] / n < 3600
+    sim.close()
+
+
+def test_argument_errors_and_async_api():
+    import ctypes as C
+    from gpu_nbody_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.bh_create(C.byref(h), 0, 0.5, 0.0025, 0.025, 16, 0) == -2          # nbodies < 1
+    assert lib.bh_create(C.byref(h), 64, 0.5, 0.0025, 0.025, 8, 0) == -2          # vote width
+    assert lib.bh_create(C.byref(h), 64, 0.5, 0.0025, 0.025, 16, 99) == -2        # device out of range
+    a = gen(U.PlummerUniverseGenerator(1), 4096)
+    sim, _ = parity.make_pair(a, counting=False)
+    buf = np.zeros(8, np.float32)
+    assert lib.bh_read(sim.handle, 99, buf.ctypes.data, 1) == -2
+    assert lib.bh_read(sim.handle, 0, buf.ctypes.data, 10 ** 9) == -2
+    assert lib.bh_calculate_force_slice(sim.handle, 8, 16) == -2                   # not a multiple of the vote width
+    assert b"vote_width" in lib.bh_last_error(sim.handle)
+    # async step + check == step
+    ref, _ = parity.make_pair(a, counting=False)
+    ref.step(2)
+    assert lib.bh_step_async(sim.handle, 2) == 0 and lib.bh_check(sim.handle) == 0
+    for k in ("posX", "velY", "accZ", "sorted"):
+        assert np.array_equal(sim.readBuffer(k, 4096).view(np.uint32), ref.readBuffer(k, 4096).view(np.uint32))
+    sim.close(); ref.close()
