@@ -148,25 +148,13 @@ def run_ours(args, rank, world, local_rank):
     n, K, W = args.bodies, args.steps, max(3, args.warmup)
     if args.gpu_gen:
         # memory-sized configurations (BASELINE configs[3], 10^8 bodies): the universe is drawn on the device
-        # (torch CUDA generator, same seed on every rank = same bytes) and handed over with bh_upload_device
-        if args.dist != "uniform":
-            raise SystemExit("--gpu-gen supports --dist uniform (RandomCubicUniverseGenerator(6): (U-0.5)*6 per axis, v = 0, m = 1/n)")
-        g = torch.Generator(device=dev); g.manual_seed(args.seed)
-        dev_arrays = [((torch.rand(n, device=dev, generator=g) - 0.5) * 6.0).contiguous() for _ in range(3)]
-        dev_arrays += [torch.zeros(n, device=dev) for _ in range(3)] + [torch.full((n,), 1.0 / n, device=dev)]
+        # (bh_generate_universe: Philox, same seed on every rank = same bytes), no host arrays at all
+        if args.dist == "disks":
+            raise SystemExit("--gpu-gen supports --dist uniform and plummer (bh_generate_universe)")
         arrays = None
-        sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.RandomCubicUniverseGenerator(6.0, args.seed), theta=THETA, eps2=EPS2, dt=DT,
-                                          vote_width=16, device=local_rank)
-        sim._lib = _lib.load()
-        import ctypes as C
-        rc = sim._lib.bh_create(C.byref(sim._sim), n, THETA, EPS2, DT, 16, local_rank)
-        if rc != 0:
-            raise SystemExit("bh_create failed: %r" % sim._lib.bh_last_error(None))
-        sim.numberOfNodes = int(sim._lib.bh_number_of_nodes(n))
-        torch.cuda.synchronize()
-        sim._check(sim._lib.bh_upload_device(sim.handle, *(t.data_ptr() for t in dev_arrays)))
-        del dev_arrays
-        torch.cuda.empty_cache()
+        sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None, theta=THETA, eps2=EPS2, dt=DT, vote_width=16, device=local_rank)
+        sim.init(None)
+        sim.generateOnDevice("cubic" if args.dist == "uniform" else "plummer", args.seed, 6.0)
     else:
         arrays = make_universe(args.dist, n, args.seed)
         sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, U.ArrayUniverseGenerator(*arrays), theta=THETA, eps2=EPS2, dt=DT, vote_width=16,
@@ -220,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
             value = n * K / (ms_total * 1e-3)
             print(json.dumps({"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic (uniform cube drawn on the device, torch CUDA generator seed %d)" % args.seed,
+                              "data": "synthetic (%s drawn on the device by bh_generate_universe, Philox seed %d)" % (args.dist, args.seed),
                               "config": {"workload": workload_name(args.dist, n), "bodies": n, "parallelism": "replicated tree, %d sorted slice(s)" % world},
                               "clocks": clocks, "gpu_launches": launches, "e2e": None, "cells_used": st["cells_used"], "max_depth": st["max_depth"],
                               "stage_ms": stage_ms}), flush=True)

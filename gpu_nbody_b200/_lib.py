@@ -100,6 +100,7 @@ def load():
         "bh_copy_vertices": (C.c_int, [p, p, p]),
         "bh_stats": (C.c_int, [p, C.POINTER(BhStats)]),
         "bh_diagnostics": (C.c_int, [p, i32, C.POINTER(BhDiag)]),
+        "bh_generate_universe": (C.c_int, [p, i32, C.c_uint64, f32, f32, f32]),
         "bh_universe_file_bodies": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
         "bh_upload_universe_file": (C.c_int, [p, C.c_char_p]),
         "bh_reset_stats": (C.c_int, [p]),

@@ -31,6 +31,7 @@
 // the force kernel bit-reproducible on the CPU.
 #pragma once
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <stdint.h>
 
 namespace bh {
@@ -99,7 +100,15 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
     __shared__ bool isLast;
     const float4 seed = node4[0];  // boundingbox.cl:44-58: every lane starts from body 0
     float mnx = seed.x, mny = seed.y, mnz = seed.z, mxx = seed.x, mxy = seed.y, mxz = seed.z;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+        const float4 p0 = node4[i], p1 = node4[i + stride], p2 = node4[i + 2 * stride], p3 = node4[i + 3 * stride];
+        mnx = fminf(fminf(mnx, p0.x), fminf(fminf(p1.x, p2.x), p3.x)); mxx = fmaxf(fmaxf(mxx, p0.x), fmaxf(fmaxf(p1.x, p2.x), p3.x));
+        mny = fminf(fminf(mny, p0.y), fminf(fminf(p1.y, p2.y), p3.y)); mxy = fmaxf(fmaxf(mxy, p0.y), fmaxf(fmaxf(p1.y, p2.y), p3.y));
+        mnz = fminf(fminf(mnz, p0.z), fminf(fminf(p1.z, p2.z), p3.z)); mxz = fmaxf(fmaxf(mxz, p0.z), fmaxf(fmaxf(p1.z, p2.z), p3.z));
+    }
+    for (; i < n; i += stride) {
         const float4 p = node4[i];
         mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x);
         mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
@@ -831,6 +840,66 @@ __global__ void copy_vertices_kernel(const float4 *__restrict__ node4, const flo
         const float4 v = velacc[2 * (size_t)i];
         vel[i] = make_float4(v.x, v.y, v.z, 1.0f);
     }
+}
+
+// ---- seeded universe generators on the device (ch.fhnw.woipv.nbody.simulation.universe.*) -----------------------
+// The reference's generators draw from the unseeded Math.random(); these draw from Philox4x32-10, one
+// subsequence per body, so a universe is a pure function of (kind, seed, n) and needs no host memory.
+// kind 0: RandomCubicUniverseGenerator.java:13-17   (U-0.5)*range per axis, v = 0, m = 1/n          (p0 = range)
+// kind 1: PlummerUniverseGenerator.java:8-41        Plummer sphere, mass-fraction cut 0.999, m = 1/n
+// kind 2: RotatingDiskGalaxyGenerator.java:17-43    disk of radius p0, velocity multiplier p1, body 0 = centre mass p2
+__device__ __forceinline__ double philox_uniform(curandStatePhilox4_32_10_t *st) { return 1.0 - curand_uniform_double(st); }  // [0,1)
+
+__global__ void __launch_bounds__(256) generate_kernel(float4 *__restrict__ node4, float4 *__restrict__ velacc,
+                                                       int *__restrict__ sorted, int n, int kind, unsigned long long seed,
+                                                       float p0, float p1, float p2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)i, 0, &st);
+    float x = 0.f, y = 0.f, z = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, mass = 1.0f / (float)n;
+    if (kind == 0) {
+        x = (float)((philox_uniform(&st) - 0.5) * p0);
+        y = (float)((philox_uniform(&st) - 0.5) * p0);
+        z = (float)((philox_uniform(&st) - 0.5) * p0);
+    } else if (kind == 1) {
+        const double kPi = 3.14159265358979323846;
+        const double rsc = (3 * kPi) / 16, vsc = sqrt(1.0 / rsc);
+        mass = (float)(1.0 / n);
+        const double r = 1.0 / sqrt(pow(philox_uniform(&st) * 0.999, -2.0 / 3.0) - 1);
+        double a, b, c, sq;
+        do {
+            a = philox_uniform(&st) * 2.0 - 1.0; b = philox_uniform(&st) * 2.0 - 1.0; c = philox_uniform(&st) * 2.0 - 1.0;
+            sq = a * a + b * b + c * c;
+        } while (sq > 1.0 || sq == 0.0);
+        double scale = rsc * r / sqrt(sq);
+        x = (float)(a * scale); y = (float)(b * scale); z = (float)(c * scale);
+        do {
+            a = philox_uniform(&st); b = philox_uniform(&st) * 0.1;
+        } while (b > a * a * pow(1 - a * a, 3.5));
+        const double v = a * sqrt(2.0 / sqrt(1 + r * r));
+        do {
+            a = philox_uniform(&st) * 2.0 - 1.0; b = philox_uniform(&st) * 2.0 - 1.0; c = philox_uniform(&st) * 2.0 - 1.0;
+            sq = a * a + b * b + c * c;
+        } while (sq > 1.0 || sq == 0.0);
+        scale = vsc * v / sqrt(sq);
+        vx = (float)(a * scale); vy = (float)(b * scale); vz = (float)(c * scale);
+    } else {
+        if (i == 0) {
+            mass = p2;  // bodiesMass[0] = centerMass, at the origin
+        } else {
+            const float r = (float)(philox_uniform(&st) * p0) + 0.05f;
+            const double alpha = philox_uniform(&st) * 2 * 3.14159265358979323846;
+            x = (float)(cos(alpha) * r); y = (float)(sin(alpha) * r);
+            z = (float)((philox_uniform(&st) - 0.5) / 8);
+            const float v0 = (float)sqrt((double)((p2 + mass) / (r * r * r))) * p1;
+            vx = y * v0; vy = -x * v0;
+        }
+    }
+    node4[i] = make_float4(x, y, z, mass);
+    velacc[2 * (size_t)i] = make_float4(vx, vy, vz, 0.0f);
+    velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    sorted[i] = 0;
 }
 
 // ---- diagnostics (GPUBH:305-365 printEnergy / printImpulse, on the device) ---------------------------

@@ -646,6 +646,17 @@ int bh_reset_stats(bh_sim *sim) {
 
 int32_t bh_number_of_bodies(bh_sim *sim) { return sim ? S(sim)->n : BH_ERR_ARG; }
 
+int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, float p1, float p2) {
+    BH_ENTER(sim);
+    if (kind < 0 || kind > 2) return fail(s, BH_ERR_ARG, "unknown universe kind %d", kind);
+    int rc = resetState(s);
+    if (rc) return rc;
+    bh::generate_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, s->sorted, s->n, kind, seed, p0, p1, p2);
+    BH_CUDA(s, cudaGetLastError());
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    return BH_OK;
+}
+
 int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
     BH_ENTER(sim);
     if (!out) return fail(s, BH_ERR_ARG, "out is NULL");

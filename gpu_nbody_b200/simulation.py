@@ -92,6 +92,8 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
         if self.theta_macro is not None:
             self._check(self._lib.bh_set_theta_macro(self._sim, float(self.theta_macro)))
         self.numberOfNodes = int(self._lib.bh_number_of_nodes(self.nbodies))  # GPUBH:130
+        if self.universeGenerator is None:  # the caller fills the buffers itself (generateOnDevice, uploadUniverseFile)
+            return
         m1 = self.numberOfNodes + 1
         host = [np.zeros(m1, dtype=np.float32) for _ in range(7)]             # GPUBH:134-142
         self.universeGenerator.generate(0, self.nbodies, *host)               # GPUBH:144
@@ -170,6 +172,11 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
         out = {k: getattr(d, k) for k, _ in d._fields_}
         out["etot"] = out["ekin"] + out["epot"]
         return out
+
+    def generateOnDevice(self, kind, seed, p0=0.0, p1=0.0, p2=0.0):
+        """Seeded generator on the device: kind "cubic" (p0 = range), "plummer", "disk" (r, velocityMultiplier, centerMass)."""
+        k = {"cubic": 0, "plummer": 1, "disk": 2}[kind]
+        self._check(self._lib.bh_generate_universe(self._sim, k, int(seed), float(p0), float(p1), float(p2)))
 
     def uploadUniverseFile(self, path):
         """SerializedUniverseGenerator without a JVM: read a .universe file natively and upload it."""

@@ -154,6 +154,14 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which);
  * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
 int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
 
+/* Seeded universe generators on the device (the reference's universe/*.java draw from the unseeded
+ * Math.random() on the host and upload): Philox4x32-10, one subsequence per body; resets the other buffers
+ * like bh_upload.  kind 0 = RandomCubicUniverseGenerator(range = p0) (RandomCubicUniverseGenerator.java:13-17),
+ * 1 = PlummerUniverseGenerator (PlummerUniverseGenerator.java:8-41), 2 = RotatingDiskGalaxyGenerator(r = p0,
+ * velocityMultiplier = p1, centerMass = p2) (RotatingDiskGalaxyGenerator.java:17-43). */
+enum bh_universe_kind { BH_UNIVERSE_RANDOM_CUBIC = 0, BH_UNIVERSE_PLUMMER = 1, BH_UNIVERSE_ROTATING_DISK = 2 };
+int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, float p1, float p2);
+
 /* printEnergy / printImpulse (GPUBH:305-365) as device reductions instead of O(N^2) host loops:
  * kinetic energy, momentum, total mass, and -- if with_potential -- the softened potential
  * -sum_{i<j} m_i m_j / sqrt(r^2 + eps2) by a tiled direct sum (the parity tests' energy formula; the

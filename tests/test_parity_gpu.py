@@ -298,3 +298,45 @@ def test_argument_errors_and_async_api():
     for k in ("posX", "velY", "accZ", "sorted"):
         assert np.array_equal(sim.readBuffer(k, 4096).view(np.uint32), ref.readBuffer(k, 4096).view(np.uint32))
     sim.close(); ref.close()
+
+
+def test_device_generators():
+    """bh_generate_universe: seeded, distribution of the reference generators, and a valid input for the step."""
+    n = 200_000
+    outs = []
+    for _ in range(2):
+        sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+        sim.init(None)
+        sim.generateOnDevice("plummer", 7)
+        outs.append([sim.readBuffer(k, n) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "mass")])
+        if len(outs) == 2:
+            sim.step(2)
+            assert sim.scalar("error") == 0 and sim.readBuffer("bodyCount")[sim.numberOfNodes] == n
+        sim.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))  # same seed, same bytes
+    x, y, z, vx, vy, vz, m = outs[0]
+    r = np.sqrt(x.astype(np.float64) ** 2 + y ** 2 + z ** 2)
+    assert abs(np.median(r) / (3 * np.pi / 16) - 1.3048) < 0.02     # Plummer half-mass radius
+    assert np.all(m == np.float32(1.0 / n)) and np.unique(np.stack([x, y, z], 1).view(np.uint32), axis=0).shape[0] == n
+    # virial-ish: 2T/|W| of the reference's Plummer model in its units is ~1
+    ek = 0.5 * float((m.astype(np.float64) * (vx.astype(np.float64) ** 2 + vy ** 2 + vz ** 2)).sum())
+    assert 0.1 < ek < 0.4
+
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+    sim.init(None)
+    sim.generateOnDevice("cubic", 3, 6.0)
+    c = np.stack([sim.readBuffer(k, n) for k in ("posX", "posY", "posZ")], 1)
+    assert c.min() >= -3.0 and c.max() <= 3.0 and abs(float(c.mean())) < 0.02 and abs(float(c.std()) - 6 / np.sqrt(12)) < 0.01
+    assert not sim.readBuffer("velX", n).any()
+    sim.generateOnDevice("disk", 5, 3.5, 1.0, 1.0)
+    d = [sim.readBuffer(k, n) for k in ("posX", "posY", "posZ", "velX", "velY", "mass")]
+    assert d[5][0] == 1.0 and d[0][0] == 0.0 and np.all(d[5][1:] == np.float32(1.0 / n))
+    rr = np.sqrt(d[0][1:].astype(np.float64) ** 2 + d[1][1:] ** 2)
+    assert rr.min() >= 0.05 - 1e-6 and rr.max() <= 3.55 + 1e-6 and np.abs(d[2]).max() <= 1 / 16 + 1e-6
+    # circular orbits: v perpendicular to r, |v| = sqrt((M+m)/r)
+    dot = d[0][1:] * d[3][1:] + d[1][1:] * d[4][1:]
+    assert np.abs(dot).max() < 1e-3
+    sim.step(1)
+    assert sim.scalar("error") == 0
+    sim.close()
