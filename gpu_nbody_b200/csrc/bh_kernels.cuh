@@ -614,10 +614,12 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     unsigned dqBase = (unsigned)__cvta_generic_to_shared(dq);
     unsigned rowLane = rowBase + 16u * (unsigned)lane;
     // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices (lane 10 only prefetches the meta word)
+    // (lanes 11-31 get a harmless duplicate of lane 0's address so that the prefetch needs no divergent branch)
     const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
                            : lane < 10 ? reinterpret_cast<const char *>(oidx) + 16 * (lane - 8)
-                                       : reinterpret_cast<const char *>(meta);
-    int laneStride = lane < 8 ? 128 : lane < 10 ? 32 : 4;
+                           : lane == 10 ? reinterpret_cast<const char *>(meta)
+                                        : reinterpret_cast<const char *>(octet);
+    int laneStride = (lane < 8 || lane > 10) ? 128 : lane < 10 ? 32 : 4;
     asm volatile("" : "+r"(rowBase), "+r"(dqBase), "+r"(rowLane), "+r"(laneStride));  // keep them in registers
     // groups with at least one existing body take part in the walk
     const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             const int ch = lds_s32(rowBase + 128u + 4u * (j));                                                         \
             sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));                                                 \
             sp += 8;                                                                                                   \
-            if (lane < 11) prefetch_l1(lane_address(laneBase, ch, laneStride));                                        \
+            prefetch_l1(lane_address(laneBase, ch, laneStride));                                                       \
         }                                                                                                              \
         if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                             \
         if (bits & ~open) { /* at least one group uses the cell as a point mass */                                    \
