@@ -256,6 +256,22 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "steps": Ke,
                     "h2d_bytes_per_step": 28 * n, "d2h_bytes_per_step": 32 * n},
             "cells_used": st["cells_used"], "max_depth": st["max_depth"]}
+    if world == 1 and n != (1 << 20) and not args.no_cpu:
+        # BASELINE configs[1] beside the headline workload: Plummer 2^20 on the same GPU, same protocol
+        n1 = 1 << 20
+        a1 = make_universe("plummer", n1, 42)
+        s1 = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n1, U.ArrayUniverseGenerator(*a1), theta=THETA, eps2=EPS2, dt=DT, vote_width=16,
+                                         device=local_rank)
+        s1.init(None)
+        s1.setStream(torch.cuda.current_stream(dev).cuda_stream)
+        s1.step(W)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        f0.record(); s1._check(lib.bh_step_async(s1.handle, K)); f1.record(); torch.cuda.synchronize()
+        s1._check(lib.bh_check(s1.handle))
+        line["configs1_plummer_1m"] = {"workload": workload_name("plummer", n1), "value": n1 * K / (f0.elapsed_time(f1) * 1e-3),
+                                       "unit": "body-steps/s", "ms_per_step": f0.elapsed_time(f1) / K}
+        s1.close()
     if world == 1:
         peak = SMS * LANES * 2 * 1.965e9 / 1e12
         peak_src = "computed 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 CUDA-core peak is not in MEASURED_PEAKS.json)"
