@@ -77,6 +77,7 @@ def load():
         "bh_set_profiling": (C.c_int, [p, i32]),
         "bh_set_counting": (C.c_int, [p, i32]),
         "bh_set_insertion_order": (C.c_int, [p, i32]),
+        "bh_set_graph": (C.c_int, [p, i32]),
         "bh_upload": (C.c_int, [p] + [p] * 7),
         "bh_upload_device": (C.c_int, [p] + [p] * 7),
         "bh_bounding_box": (C.c_int, [p]),

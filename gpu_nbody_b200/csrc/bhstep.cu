@@ -53,6 +53,11 @@ struct Sim {
     int nranks = 1, rank = 0, accPhase = 0;
     bool p2p = false;
     float4 *peerAcc[bh::kMaxPeers] = {};
+    // CUDA graph of one step
+    bool useGraph = true;
+    cudaGraphExec_t graphExec = nullptr;
+    cudaStream_t graphStream = nullptr;
+    int graphInsertion = -1;
     std::string lastError;
 };
 
@@ -189,8 +194,40 @@ int finish(Sim *s) {
     return BH_OK;
 }
 
+// One step = six launches with fixed arguments once a sorted order exists: captured once into a CUDA graph and
+// replayed (one launch call per step instead of six; matters for small universes such as the reference's 32 768-body
+// default, where a step is a few hundred microseconds).  Not used while per-stage events or counters are on.
+int graphStep(Sim *s) {
+    if (!s->graphExec || s->graphStream != s->stream || s->graphInsertion != s->insertionOrder) {
+        if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        BH_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = BH_OK;
+        for (int st = 0; st < BH_NUM_STAGES && rc == BH_OK; ++st) rc = launchStage(s, st);
+        const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != BH_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc != BH_OK ? rc : fail(s, BH_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+        }
+        for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st]--;  // the capture did not run anything
+        const cudaError_t ei = cudaGraphInstantiate(&s->graphExec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { s->graphExec = nullptr; return fail(s, BH_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+        s->graphStream = s->stream;
+        s->graphInsertion = s->insertionOrder;
+    }
+    BH_CUDA(s, cudaGraphLaunch(s->graphExec, s->stream));
+    for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st]++;
+    return BH_OK;
+}
+
 int stepAsync(Sim *s, int nsteps) {
     for (int i = 0; i < nsteps; ++i) {
+        if (s->useGraph && !s->profiling && !s->counting && s->haveSorted) {
+            int rc = graphStep(s);
+            if (rc) return rc;
+            continue;
+        }
         const bool prof = s->profiling && s->evSteps < kProfSteps;
         if (prof && !s->evCreated) {
             for (auto &row : s->ev)
@@ -333,6 +370,7 @@ void bh_destroy(bh_sim *sim) {
     Sim *s = S(sim);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
     for (int r = 0; r < s->nranks; ++r)
         if (s->p2p && r != s->rank && s->peerAcc[r]) cudaIpcCloseMemHandle(s->peerAcc[r]);
     cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
@@ -353,6 +391,7 @@ void bh_destroy(bh_sim *sim) {
 
 int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
     BH_ENTER(sim);
+    if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }  // kernel arguments change
     s->thetaMacro = theta_macro;
     return BH_OK;
 }
@@ -380,6 +419,12 @@ int bh_set_profiling(bh_sim *sim, int32_t on) {
 int bh_set_counting(bh_sim *sim, int32_t on) {
     BH_ENTER(sim);
     s->counting = on != 0;
+    return BH_OK;
+}
+
+int bh_set_graph(bh_sim *sim, int32_t on) {
+    BH_ENTER(sim);
+    s->useGraph = on != 0;
     return BH_OK;
 }
 

@@ -161,6 +161,7 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
     # ---- options / diagnostics --------------------------------------------------------
     def setProfiling(self, on=True): self._check(self._lib.bh_set_profiling(self._sim, int(on)))
     def setCounting(self, on=True): self._check(self._lib.bh_set_counting(self._sim, int(on)))
+    def setGraph(self, on=True): self._check(self._lib.bh_set_graph(self._sim, int(on)))
     def setInsertionOrder(self, mode): self._check(self._lib.bh_set_insertion_order(self._sim, int(mode)))
     def setStream(self, cuda_stream): self._check(self._lib.bh_set_stream(self._sim, C.c_void_p(cuda_stream)))
     def resetStats(self): self._check(self._lib.bh_reset_stats(self._sim))

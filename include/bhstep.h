@@ -97,6 +97,8 @@ int bh_set_counting(bh_sim *sim, int32_t on);
 /* Order in which build_tree inserts bodies: 0 = index order, 1 = previous step's
  * sorted (DFS / Morton-like) order.  The resulting tree is identical. */
 int bh_set_insertion_order(bh_sim *sim, int32_t mode);
+/* 1 (default) = bh_step replays one captured CUDA graph per step (six kernels, fixed arguments); 0 = six launches. */
+int bh_set_graph(bh_sim *sim, int32_t on);
 
 /* createBuffer(CL_MEM_COPY_HOST_PTR, ...) for the seven generator outputs (GPUBH:155-170):
  * caller-owned host SoA arrays of length nbodies are copied; all other buffers are
