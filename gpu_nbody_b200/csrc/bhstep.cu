@@ -201,7 +201,11 @@ int graphStep(Sim *s) {
     if (!s->graphExec || s->graphStream != s->stream || s->graphInsertion != s->insertionOrder) {
         if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
         cudaGraph_t graph = nullptr;
-        BH_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();    // e.g. a stream that cannot be captured: plain launches from now on
+            s->useGraph = false;
+            return BH_ERR_ARG;     // tells stepAsync to launch this step the ordinary way
+        }
         int rc = BH_OK;
         for (int st = 0; st < BH_NUM_STAGES && rc == BH_OK; ++st) rc = launchStage(s, st);
         const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
@@ -223,10 +227,11 @@ int graphStep(Sim *s) {
 
 int stepAsync(Sim *s, int nsteps) {
     for (int i = 0; i < nsteps; ++i) {
-        if (s->useGraph && !s->profiling && !s->counting && s->haveSorted) {
+        // (the legacy default stream cannot be captured)
+        if (s->useGraph && !s->profiling && !s->counting && s->haveSorted && s->stream != nullptr) {
             int rc = graphStep(s);
-            if (rc) return rc;
-            continue;
+            if (rc == BH_OK) continue;
+            if (s->useGraph) return rc;  // a real failure; otherwise capture was refused and the graph is now off
         }
         const bool prof = s->profiling && s->evSteps < kProfSteps;
         if (prof && !s->evCreated) {

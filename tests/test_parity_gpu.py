@@ -340,3 +340,22 @@ def test_device_generators():
     sim.step(1)
     assert sim.scalar("error") == 0
     sim.close()
+
+
+def test_step_on_the_default_stream_and_on_a_torch_stream():
+    """bh_set_stream with CUDA's default stream (NULL: cannot be graph-captured) and with a torch side stream."""
+    import torch
+    n = 8192
+    a = gen(U.PlummerUniverseGenerator(6), n)
+    ref, _ = parity.make_pair(a, counting=False)
+    ref.step(4)
+    want = [ref.readBuffer(k, n) for k in ("posX", "velY", "sorted")]
+    ref.close()
+    side = torch.cuda.Stream()
+    for handle in (0, side.cuda_stream):
+        sim, _ = parity.make_pair(a, counting=False)
+        sim.setStream(handle)
+        sim.step(4)
+        for w, k in zip(want, ("posX", "velY", "sorted")):
+            assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), w.view(np.uint32))
+        sim.close()
