@@ -156,7 +156,7 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which);
  * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
 int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
 
-/* Seeded universe generators on the device (the reference's universe/*.java draw from the unseeded
+/* Seeded universe generators on the device (the reference's universe generators draw from the unseeded
  * Math.random() on the host and upload): Philox4x32-10, one subsequence per body; resets the other buffers
  * like bh_upload.  kind 0 = RandomCubicUniverseGenerator(range = p0) (RandomCubicUniverseGenerator.java:13-17),
  * 1 = PlummerUniverseGenerator (PlummerUniverseGenerator.java:8-41), 2 = RotatingDiskGalaxyGenerator(r = p0,
