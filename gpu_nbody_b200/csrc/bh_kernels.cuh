@@ -704,9 +704,17 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         }
         const unsigned brow = rowBase + 16u * (unsigned)ncell;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // then child bodies: always used (:145 child < NBODIES)
-            if (j >= nbody) break;
-            const float4 c0 = lds_v4(brow + 16u * j);
+        for (int j = 0; j < 8; j += 2) {  // then child bodies, also two at a time: always used (:145 child < NBODIES)
+            if (j + 2 > nbody) break;
+            const float4 c0 = lds_v4(brow + 16u * j), c1 = lds_v4(brow + 16u * (j + 1));
+            BH_DIST(c0, 0)
+            BH_DIST(c1, 1)
+            force_accumulate(dx0, dy0, dz0, r20, __fmul_rn(c0.w, mscale), ax, ay, az);
+            force_accumulate(dx1, dy1, dz1, r21, __fmul_rn(c1.w, mscale), ax, ay, az);
+            if (COUNT && mine) nInter += 2 * nact;
+        }
+        if (nbody & 1) {
+            const float4 c0 = lds_v4(brow + 16u * (unsigned)(nbody - 1));
             BH_DIST(c0, 0)
             force_accumulate(dx0, dy0, dz0, r20, __fmul_rn(c0.w, mscale), ax, ay, az);
             if (COUNT && mine) nInter += nact;
