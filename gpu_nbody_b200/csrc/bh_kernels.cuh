@@ -507,11 +507,10 @@ constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 
 // -- per-child global loads miss L1 on every second child (32-byte sectors) and
 // each miss costs an L2 round trip -- and the children are consumed with
 // broadcast LDS.128: child cells first (7 packed fp32 ops, one ballot; a second
-// ballot and the push only if some body is too near), then child bodies.
+// ballot and the push only if some body is too near), then child bodies.  (An L1
+// prefetch of pushed cells was measured and dropped: 2 % slower than none.)
 constexpr int kForce2Threads = 128;
 constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float rsqrt_fast(float x) {
     // r^2 >= EPSILON > 0 is never subnormal: the bare MUFU.RSQ (2 ulp, calculateforce.cl:146 allows rsqrt's 2 ulp)
@@ -613,13 +612,10 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     unsigned rowBase = (unsigned)__cvta_generic_to_shared(stage[warp]);
     unsigned dqBase = (unsigned)__cvta_generic_to_shared(dq);
     unsigned rowLane = rowBase + 16u * (unsigned)lane;
-    // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices (lane 10 only prefetches the meta word)
-    // (lanes 11-31 get a harmless duplicate of lane 0's address so that the prefetch needs no divergent branch)
-    const char *laneBase = lane < 8    ? reinterpret_cast<const char *>(octet + lane)
-                           : lane < 10 ? reinterpret_cast<const char *>(oidx) + 16 * (lane - 8)
-                           : lane == 10 ? reinterpret_cast<const char *>(meta)
-                                        : reinterpret_cast<const char *>(octet);
-    int laneStride = (lane < 8 || lane > 10) ? 128 : lane < 10 ? 32 : 4;
+    // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices
+    const char *laneBase = lane < 8 ? reinterpret_cast<const char *>(octet + lane)
+                                    : reinterpret_cast<const char *>(oidx) + 16 * ((lane - 8) & 1);
+    int laneStride = lane < 8 ? 128 : 32;
     asm volatile("" : "+r"(rowBase), "+r"(dqBase), "+r"(rowLane), "+r"(laneStride));  // keep them in registers
     // groups with at least one existing body take part in the walk
     const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
@@ -666,7 +662,6 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             const int ch = lds_s32(rowBase + 128u + 4u * (j));                                                         \
             sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));                                                 \
             sp += 8;                                                                                                   \
-            prefetch_l1(lane_address(laneBase, ch, laneStride));                                                       \
         }                                                                                                              \
         if (COUNT && (near & gmMine) != 0u) nOpen += nact;                                                             \
         if (bits & ~open) { /* at least one group uses the cell as a point mass */                                    \
