@@ -95,6 +95,18 @@ def make(name):
           "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")), flush=True)
 
 
+def make_trajectory():
+    """BASELINE configs[0]: 10 steps of the bundled universe with the reference kernels (about 4 minutes)."""
+    arrays = bundled("sphericaluniverse1")
+    n = arrays[0].size
+    ref = refshim.run(arrays, steps=10, stop_after="integrate", fma=False, theta05=True)
+    sel = np.arange(0, n, 8)
+    np.savez_compressed(os.path.join(HERE, "ref_sphericaluniverse1_theta05_10steps.npz"), n=np.int32(n), steps=np.int32(10),
+                        theta_macro=np.float32(0.25), eps2=np.float32(0.0025), dt=np.float32(0.025), body_sel=sel.astype(np.int32),
+                        step=ref["step"], maxDepth=ref["maxDepth"], error=ref["error"],
+                        **{"integ_" + k: ref[k][:n][sel] for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "accY", "accZ")})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -104,3 +116,5 @@ if __name__ == "__main__":
     for nm in FIXTURES:
         if a.only is None or a.only == nm:
             make(nm)
+    if a.only in (None, "trajectory"):
+        make_trajectory()

@@ -76,3 +76,20 @@ def check_after_integrate(buf, g):
     bsel = g["body_sel"]
     for k in ("posX", "posY", "posZ", "velX", "velY", "velZ"):
         np.testing.assert_allclose(np.asarray(buf[k])[:n][bsel], g["integ_" + k], rtol=1e-5, atol=1e-6, err_msg="integrate " + k)
+
+
+TRAJECTORY_FIXTURE = "ref_sphericaluniverse1_theta05_10steps"  # BASELINE configs[0]: the bundled universe, theta = 0.5, 10 steps
+
+
+def check_trajectory(buf, g):
+    """State after `steps` full steps against the reference kernels' state (every 8th body)."""
+    n = int(g["n"])
+    sel = g["body_sel"]
+    assert int(np.asarray(buf["step"]).ravel()[0]) == int(g["step"][0]) and int(np.asarray(buf["maxDepth"]).ravel()[0]) == int(g["maxDepth"][0])
+    for k in ("posX", "posY", "posZ", "velX", "velY", "velZ"):
+        np.testing.assert_allclose(np.asarray(buf[k])[:n][sel], g["integ_" + k], rtol=0, atol=1e-6, err_msg=k)
+    a = np.stack([np.asarray(buf[k])[:n][sel] for k in ("accX", "accY", "accZ")], axis=1).astype(np.float64)
+    r = np.stack([g["integ_" + k] for k in ("accX", "accY", "accZ")], axis=1).astype(np.float64)
+    err = np.linalg.norm(a - r, axis=1) / np.maximum(np.linalg.norm(r, axis=1), 1e-30)
+    assert err.max() <= ACC_RTOL, "acceleration after %d steps vs reference: max rel err %g" % (int(g["steps"]), err.max())
+    return float(err.max())

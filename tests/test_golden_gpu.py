@@ -25,3 +25,16 @@ def test_cuda_matches_reference_kernels(name):
     sim.integrate()
     gc.check_after_integrate({k: sim.readBuffer(k) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ")}, g)
     sim.close()
+
+
+def test_cuda_ten_steps_of_the_bundled_universe():
+    """BASELINE configs[0]: sphericaluniverse1, theta = 0.5, 10 steps, against the reference kernels' own 10 steps."""
+    g = gc.load(gc.TRAJECTORY_FIXTURE)
+    arrays = gc.bundled_inputs("sphericaluniverse1")
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, 32768, U.ArrayUniverseGenerator(*arrays), eps2=float(g["eps2"]), dt=float(g["dt"]),
+                                      theta_macro=float(g["theta_macro"]))
+    sim.init(None)
+    sim.step(10)
+    err = gc.check_trajectory({k: sim.readBuffer(k) for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "accY", "accZ", "step", "maxDepth")}, g)
+    assert err < 1e-5
+    sim.close()

@@ -101,3 +101,13 @@ def test_overflow_and_depth_errors():
         a[k][10] = a[k][3]  # coincident bodies: buildtree.cl:112-119
     o = oracle.OracleSim(64, *a)
     assert o.step(1) == 1 and o.error[0] == 1 and o.bottom[0] == o.m
+
+
+@pytest.mark.parametrize("fma", [0, 1])
+def test_oracle_ten_steps_of_the_bundled_universe(fma):
+    """BASELINE configs[0]: sphericaluniverse1, theta = 0.5, 10 steps, against the reference kernels' own 10 steps."""
+    g = gc.load(gc.TRAJECTORY_FIXTURE)
+    o = oracle.OracleSim(32768, *gc.bundled_inputs("sphericaluniverse1"), theta_macro=float(g["theta_macro"]), eps2=float(g["eps2"]),
+                         dt=float(g["dt"]), fma_policy=fma)
+    assert o.step(10) == 0
+    gc.check_trajectory(o.buf, g)
