@@ -359,3 +359,22 @@ def test_step_on_the_default_stream_and_on_a_torch_stream():
         for w, k in zip(want, ("posX", "velY", "sorted")):
             assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), w.view(np.uint32))
         sim.close()
+
+
+def test_upload_from_device_memory():
+    """bh_upload_device: inputs already resident in HBM (torch tensors) give the same state as bh_upload."""
+    import torch
+    n = 5000
+    a = gen(U.PlummerUniverseGenerator(12), n)
+    ref, _ = parity.make_pair(a, counting=False)
+    ref.step(2)
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+    sim.init(None)
+    dev = [torch.from_numpy(x).cuda() for x in a]
+    torch.cuda.synchronize()
+    sim._check(sim._lib.bh_upload_device(sim.handle, *(t.data_ptr() for t in dev)))
+    assert sim._lib.bh_use_private_stream(sim.handle) == 0
+    sim.step(2)
+    for k in ("posX", "posY", "velZ", "accX", "sorted"):
+        assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), ref.readBuffer(k, n).view(np.uint32))
+    sim.close(); ref.close()
