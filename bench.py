@@ -92,6 +92,7 @@ def cpu_oracle_sample(arrays, n, budget_s=20.0, steps=1, warmup=0):
     the force walk on `sample` sorted bodies starting at rotating offsets, the
     integrate on all bodies; per-step time = tree + force * n/sample + integrate."""
     import oracle
+    oracle.use_all_cores()
     orc = oracle.OracleSim(n, *arrays, theta=THETA, eps2=EPS2, dt=DT, vote_width=16, fma_policy=1)
     t = time.perf_counter(); orc.bounding_box(); orc.build_tree(); orc.summarize(); orc.sort(); t_tree = time.perf_counter() - t
     # calibrate the sample so that one force sample takes about budget_s / (steps + warmup)

@@ -62,6 +62,8 @@ def lib():
         _LIB.bho_direct_acc.restype = None
         _LIB.bho_direct_acc.argtypes = [C.c_int32] + [C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_int32] + [C.c_void_p] * 3
         _LIB.bho_num_threads.restype = C.c_int32
+        _LIB.bho_set_num_threads.restype = None
+        _LIB.bho_set_num_threads.argtypes = [C.c_int32]
     return _LIB
 
 
@@ -71,6 +73,13 @@ def number_of_nodes(nbodies: int) -> int:
 
 def num_threads() -> int:
     return int(lib().bho_num_threads())
+
+
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().bho_set_num_threads(n)
+    return num_threads()
 
 
 class OracleSim:

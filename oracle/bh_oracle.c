@@ -464,6 +464,15 @@ void bho_direct_acc(int32_t n, const float *x, const float *y, const float *z, c
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs ask for all host cores explicitly. */
+void bho_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int32_t bho_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
