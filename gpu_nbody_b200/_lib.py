@@ -34,7 +34,8 @@ class BhStats(C.Structure):
     _fields_ = [("nbodies", C.c_int32), ("number_of_nodes", C.c_int32), ("cells_used", C.c_int32),
                 ("max_depth", C.c_int32), ("step", C.c_int32), ("error", C.c_int32),
                 ("steps_timed", C.c_int64), ("stage_ms", C.c_double * 6), ("stage_launches", C.c_int64 * 6),
-                ("interactions", C.c_int64), ("opens", C.c_int64)]
+                ("interactions", C.c_int64), ("opens", C.c_int64), ("barrier_ms", C.c_double), ("deep_walk", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -91,6 +92,14 @@ def load():
         "bh_check": (C.c_int, [p]),
         "bh_calculate_force_slice": (C.c_int, [p, i32, i32]),
         "bh_apply_acceleration": (C.c_int, [p]),
+        "bh_finish_async": (C.c_int, [p]),
+        "bh_ipc_clear_peers": (C.c_int, [p]),
+        "bh_set_slice": (C.c_int, [p, i32, i32]),
+        "bh_peer_barrier": (C.c_int, [p]),
+        "bh_set_force_deep_walk": (C.c_int, [p, i32]),
+        "bh_copy_vertices_device": (C.c_int, [p, p, p]),
+        "bh_set_vertex_buffers": (C.c_int, [p, p, p]),
+        "bh_write_universe_file": (C.c_int, [p, C.c_char_p]),
         "bh_acc_sorted_device_ptr": (p, [p]),
         "bh_ipc_export": (C.c_int, [p, p]),
         "bh_ipc_set_peers": (C.c_int, [p, i32, i32, p]),

@@ -5,24 +5,33 @@
 //   build_kernel      <- kernels/nbody/buildtree.cl
 //   summarize_kernel  <- kernels/nbody/summarizetree.cl
 //   sort_kernel       <- kernels/nbody/sort.cl
-//   force2_kernel     <- kernels/nbody/calculateforce.cl
-//   integrate_kernel  <- kernels/nbody/integrate.cl
+//   walk_kernel       <- kernels/nbody/calculateforce.cl   (deep_walk_kernel: fallback for very deep trees / 32-wide votes)
+//   finish_kernel     <- calculateforce.cl:174-185 (velocity correction) + kernels/nbody/integrate.cl
 // They reproduce the reference's *results* (see DESIGN.md for the parity classes),
 // not its code: the data layout, work decomposition and synchronisation are
 // designed for B200.
 //
-// HBM layout (N bodies, M = number of nodes, NC = M - N + 1 cell slots):
-//   node4  float4[M+1]   {x, y, z, mass}; bodies 0..N-1, cells N..M, root = M.
-//                        During build a cell holds its geometric centre and
-//                        mass = -1; summarise overwrites it with {COM, mass}.
-//   velacc float4[2N]    {vx,vy,vz,0},{ax,ay,az,0} per body: one 32-byte sector.
-//   child  int[8*NC]     child[(cell-N)*8 + k]; -1 empty, -2 locked, <N body, >=N cell
-//   octet  float4[8*NC]  the force walk's record of a cell: copies of its children's node4
-//   oidx   int[8*NC]     records, child cells first, then child bodies (128-byte line), the
-//   meta   int[NC]       child cells' indices minus N, and #cells | #bodies << 4.  Written by summarise.
-//   start, count int[NC] `start` and `bodyCount` of the reference; count doubles
-//                        as the "summarised" flag (-1 = not yet).
-//   sorted int[N]        bodies in tree (DFS) order.
+// HBM layout (N bodies, M = number of nodes, NC = M - N + 1 cell slots).  Bodies are
+// stored PHYSICALLY in the previous step's tree (DFS) order: "slot" k holds the body
+// that was k-th in sorted[] when the last step finished; the host's numbering of
+// that body travels with it (origId).  All body arrays are double buffered; the
+// fused finish kernel reads slot perm[k] of the current buffers and writes slot k
+// of the other ones.
+//   body4  float4[2][N]   {x, y, z, mass} per slot
+//   velacc float4[2][2N]  {vx,vy,vz,origId (int bits)},{ax,ay,az,0} per slot: one 32-byte sector
+//   cell4  float4[NC]     cell c at [c-N]; geometric centre and mass = -1 during build,
+//                         {COM, mass} after summarise; root = cell M
+//   child  int[8*NC]      child[(cell-N)*8 + k]; -1 empty, -2 locked, <N body slot, >=N cell
+//   octet  float4[8*NC]   the force walk's record of a cell, written by summarise: copies of its
+//   ometa  int2[8*NC]     children's {x,y,z,mass}, child cells first, then child bodies, and per child
+//                         {opening threshold dq[level] as float bits, walk entry}: walk entry of a cell =
+//                         (cell-N) | (#children-1) << 27; bodies have threshold -1 (always accepted) and entry -1
+//   meta   int[NC]        #child cells | #child bodies << 4 (deep walk kernel)
+//   start  int[NC]        `start` of the reference
+//   count  int[NC]        bodyCount | (#children-1) << 28; -1 = not summarised yet
+//   parent, arrived int[NC]  parent pointer; level << 16 | #child cells << 8 | reports received (counter-driven summarise)
+//   perm   int[N]         sort's output: perm[k] = slot of the k-th body in tree order (sorted[] = origId[perm[k]])
+//   acc    float4[2][N+pad] accelerations in tree order (written by the walk; the multi-GPU all-gather buffer)
 //
 // Floating-point policy (DESIGN.md "FMA policy"): every source-level x*y+z of the
 // reference is one fmaf, everything else a separately rounded IEEE operation,
@@ -39,6 +48,8 @@ namespace bh {
 constexpr int kMaxDepth = 64;       // MAXDEPTH, calculateforce.cl:12
 constexpr int kLock = -2;           // LOCK, buildtree.cl:8
 constexpr int kSpinBudget = 1 << 24;  // polls before a device-side wait gives up (error = 2)
+constexpr int kEntryMask = 0x7ffffff;  // cell - N of a walk entry (27 bits: NC <= 2^27)
+constexpr int kCountMask = 0xfffffff;  // bodyCount of a count word (28 bits)
 
 struct Scalars {
     int step;         // init -1 (GPUBH:165)
@@ -47,12 +58,15 @@ struct Scalars {
     int maxDepth;     // init 1, running max (buildtree.cl:199)
     int bottom;
     int error;
-    int pad0, pad1;
+    int deep;         // the walk ran out of shared-memory stack: deep_walk_kernel redoes the stage
+    int rootEntry;    // walk entry of the root cell (written by summarise)
     unsigned long long interactions;
     unsigned long long opens;
 };
 
 // ---- memory-model helpers -------------------------------------------------
+// Cross-thread data inside a kernel is read with strong (L2) loads; publication is a release store / release atomic
+// (MEMBAR.ALL.GPU, no L1 invalidate -- __threadfence() is fence.sc = MEMBAR.SC.GPU + CCTL.IVALL on sm_100).
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -68,6 +82,16 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
 }
 __device__ __forceinline__ void st_relaxed(int *p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int *p, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ int atom_add_acquire(int *p, int v) {
+    int old;
+    asm volatile("atom.acquire.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 
 __device__ __forceinline__ int octant(float cx, float cy, float cz, float bx, float by, float bz) {
@@ -92,24 +116,25 @@ __device__ __forceinline__ void warp_minmax(float &mnx, float &mny, float &mnz, 
     }
 }
 
-__global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__ node4, int *__restrict__ child,
-                                                            int *__restrict__ start, int *__restrict__ count,
-                                                            int *__restrict__ arrived, float *__restrict__ partials,
-                                                            Scalars *__restrict__ sc, int n, int m) {
+// (boundingbox.cl:44-58 seeds every lane with body 0; min/max do not depend on the seed, slot 0 is used)
+__global__ void __launch_bounds__(kBboxThreads) bbox_kernel(const float4 *__restrict__ body4, float4 *__restrict__ cell4,
+                                                            int *__restrict__ child, int *__restrict__ start,
+                                                            int *__restrict__ count, int *__restrict__ arrived,
+                                                            float *__restrict__ partials, Scalars *__restrict__ sc, int n, int m) {
     __shared__ float red[6][kBboxThreads / 32];
     __shared__ bool isLast;
-    const float4 seed = node4[0];  // boundingbox.cl:44-58: every lane starts from body 0
+    const float4 seed = body4[0];
     float mnx = seed.x, mny = seed.y, mnz = seed.z, mxx = seed.x, mxy = seed.y, mxz = seed.z;
     const int stride = gridDim.x * blockDim.x;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
-        const float4 p0 = node4[i], p1 = node4[i + stride], p2 = node4[i + 2 * stride], p3 = node4[i + 3 * stride];
+        const float4 p0 = body4[i], p1 = body4[i + stride], p2 = body4[i + 2 * stride], p3 = body4[i + 3 * stride];
         mnx = fminf(fminf(mnx, p0.x), fminf(fminf(p1.x, p2.x), p3.x)); mxx = fmaxf(fmaxf(mxx, p0.x), fmaxf(fmaxf(p1.x, p2.x), p3.x));
         mny = fminf(fminf(mny, p0.y), fminf(fminf(p1.y, p2.y), p3.y)); mxy = fmaxf(fmaxf(mxy, p0.y), fmaxf(fmaxf(p1.y, p2.y), p3.y));
         mnz = fminf(fminf(mnz, p0.z), fminf(fminf(p1.z, p2.z), p3.z)); mxz = fmaxf(fmaxf(mxz, p0.z), fmaxf(fmaxf(p1.z, p2.z), p3.z));
     }
     for (; i < n; i += stride) {
-        const float4 p = node4[i];
+        const float4 p = body4[i];
         mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x);
         mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
         mnz = fminf(mnz, p.z); mxz = fmaxf(mxz, p.z);
@@ -152,24 +177,25 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
         const float rz = __fmul_rn(0.5f, __fadd_rn(mnz, mxz));
         sc->radius = __fmul_rn(0.5f, fmaxf(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny)), __fsub_rn(mxz, mnz)));
         sc->bottom = m;
-        node4[m] = make_float4(rx, ry, rz, -1.0f);
+        cell4[m - n] = make_float4(rx, ry, rz, -1.0f);
         start[m - n] = 0;
         count[m - n] = -1;
-        arrived[m - n] = 0;
+        arrived[m - n] = 0;  // level 0, no child cells yet, no reports
+        sc->deep = 0;
         sc->step = sc->step + 1;
     }
 }
 
 // ---- 2. tree build ------------------------------------------------------------
 // buildtree.cl: concurrent insertion; a child slot is locked by CAS to -2 while a
-// leaf is split, the finished sub-tree is published after a device fence.  The
+// leaf is split, the finished sub-tree is published by a release store.  The
 // tree *shape* is a function of the positions and the root box only; cell
 // numbers depend on the allocation race (as in the reference).  Bodies are
-// visited through `order` (previous step's sorted[] = spatial order) when given.
+// inserted in slot order, i.e. in the previous step's tree order: the loads of
+// a lane's run are sequential and its consecutive bodies are spatial neighbours.
 //
-// B200 design, all of it about latency (the kernel issues < 20 % of its slots):
-//  * Every lane owns a contiguous run of the insertion order, so the body it
-//    inserts next is its spatial neighbour.  The lane remembers the path of its
+// B200 design, all of it about latency (the kernel issues < 25 % of its slots):
+//  * Every lane owns a contiguous run of slots.  The lane remembers the path of its
 //    previous body (cells never move or disappear during a build) and replays it
 //    without touching memory -- the octant tests use centres recomputed with the
 //    creation formula, same operands, same bits -- so only the last level or two
@@ -181,16 +207,20 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(float4 *__restrict__
 //    atomics, about 2 ms at N = 10^7) and build their whole chain in that round.
 //    Indices still decrease in allocation order, so a child cell always has a
 //    lower index than its parent, which sort relies on.
+//  * Memory model: a new sub-tree is written with ordinary stores and published by
+//    st.release.gpu into the locked slot (buildtree.cl:173-180); other threads
+//    reach it only through that slot and read it with strong (ld.relaxed.gpu, L2)
+//    loads whose addresses depend on the value loaded from the slot.
 constexpr int kBuildThreads = 256;
 constexpr int kPathCap = 24;  // remembered levels per lane (24 KB of shared memory per CTA); deeper levels are loaded
 
-__global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict__ node4, int *child,
-                                                              int *__restrict__ start, int *__restrict__ count,
-                                                              int *__restrict__ parent, int *__restrict__ arrived,
-                                                              const int *__restrict__ order, Scalars *sc, int n, int m) {
+__global__ void __launch_bounds__(kBuildThreads) build_kernel(const float4 *__restrict__ body4, float4 *__restrict__ cell4,
+                                                              int *child, int *__restrict__ start, int *__restrict__ count,
+                                                              int *__restrict__ parent, int *__restrict__ arrived, Scalars *sc,
+                                                              int n, int m) {
     constexpr unsigned kFull = 0xffffffffu;
     const float radius = sc->radius;
-    const float4 root = node4[m];
+    const float4 root = cell4[m - n];
     const int lane = threadIdx.x & 31;
     const int threadsTotal = gridDim.x * blockDim.x;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,8 +246,8 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
         float4 q = root;
         if (busy) {
             if (fresh) {
-                body = order ? order[i] : i;
-                p = node4[body];
+                body = i;
+                p = body4[body];
                 node = m; depth = 1; r = radius;
                 cx = root.x; cy = root.y; cz = root.z;
                 path = octant(cx, cy, cz, p.x, p.y, p.z);
@@ -260,7 +290,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                     busy = ++i < iEnd;
                 } else {  // buildtree.cl:102-180: count the cells that separate the two bodies
                     oldBody = ch;
-                    q = node4[ch];
+                    q = body4[ch];
                     float tr = r, tx = cx, ty = cy, tz = cz;
                     int tp = path;
                     for (;;) {
@@ -311,13 +341,14 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                         cx = __fadd_rn(__fsub_rn(cx, r), ox);  // buildtree.cl:134-136, left to right
                         cy = __fadd_rn(__fsub_rn(cy, r), oy);
                         cz = __fadd_rn(__fsub_rn(cz, r), oz);
-                        node4[cell] = make_float4(cx, cy, cz, -1.0f);
+                        cell4[cell - n] = make_float4(cx, cy, cz, -1.0f);
                         start[cell - n] = -1;
                         count[cell - n] = -1;
                         parent[cell - n] = cur;  // for the counter-driven summarise
                         const int qPath = octant(cx, cy, cz, q.x, q.y, q.z);
                         const int pPath = octant(cx, cy, cz, p.x, p.y, p.z);
-                        arrived[cell - n] = (qPath == pPath) ? (1 << 16) : 0;  // (#child cells << 16) | reports received
+                        // level << 16 | #child cells << 8 | reports received; the new cell's level is depth - 1 (root = 0)
+                        arrived[cell - n] = ((depth - 1) << 16) | ((qPath == pPath) ? (1 << 8) : 0);
                         int *row = child + (size_t)(cell - n) * 8;
                         const int4 empty = make_int4(-1, -1, -1, -1);
                         reinterpret_cast<int4 *>(row)[0] = empty;
@@ -336,9 +367,8 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
                     pathLen = min(depth, kPathCap);
                     node = cur;
                     path = curPath;
-                    atomicAdd(arrived + (node0 - n), 1 << 16);  // the leaf's cell gains a child cell
-                    __threadfence();          // :173 publish the sub-tree ...
-                    st_relaxed(slot, patch);  // :180 ... by replacing the lock
+                    atomicAdd(arrived + (node0 - n), 1 << 8);  // the leaf's cell gains a child cell
+                    st_release(slot, patch);  // :173-180 publish the sub-tree by replacing the lock
                     localMaxDepth = max(localMaxDepth, depth);
                     fresh = true;
                     busy = ++i < iEnd;
@@ -357,33 +387,51 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(float4 *__restrict
 // order and spins on children that are not ready; on 10^7 bodies most threads
 // then sit in long parent-child chains.  Here the pass is counter driven and
 // never waits: every cell collects one report per child cell plus one from its
-// own thread (`arrived`: build keeps the number of child cells in the high half,
-// reports count up in the low half; a small array that stays in L2); whoever
-// reports last summarises the cell, reports to the parent and climbs on.  Children are summed in octant order,
+// own thread (`arrived`: build keeps the number of child cells in bits 8-15,
+// reports count up in bits 0-7; a small array that stays in L2); whoever
+// reports last summarises the cell, reports to the parent and climbs on.  A
+// report is one atom.add.acq_rel.gpu: release for the record just written,
+// acquire for the siblings' records.  Children are summed in octant order,
 // which makes the result independent of timing and bit-identical to the oracle.
-// The summarising thread also writes the force walk's record of the cell.
+// The summarising thread also writes the force walk's record of the cell,
+// including the opening threshold of its children (calculateforce.cl:52-67:
+// dq[level] = radius^2 * 0.25^level / THETA + EPSILON, the same iteration).
 constexpr int kSummThreads = 256;
 
-__global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__restrict__ node4, int *__restrict__ child,
-                                                                 float4 *__restrict__ octet, int *__restrict__ oidx,
-                                                                 int *__restrict__ meta, int *__restrict__ count,
-                                                                 const int *__restrict__ parent, int *arrived, Scalars *sc,
-                                                                 int n, int m) {
+__device__ __forceinline__ void fill_dq(float *dq, const Scalars *sc, float thetaMacro, float eps) {
+    // calculateforce.cl:52-67
+    const float radius = sc->radius;
+    const int maxDepth = min(sc->maxDepth, kMaxDepth);
+    float v = __fmul_rn(radius, radius);
+    if (thetaMacro > 0.0f) v = __fdiv_rn(v, thetaMacro);
+    for (int i = 0; i < maxDepth; ++i) {
+        dq[i] = __fadd_rn(v, eps);
+        v = __fmul_rn(0.25f, v);
+    }
+}
+
+__global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(const float4 *__restrict__ body4, float4 *__restrict__ cell4,
+                                                                 int *__restrict__ child, float4 *__restrict__ octet,
+                                                                 int2 *__restrict__ ometa, int *__restrict__ meta,
+                                                                 int *__restrict__ count, const int *__restrict__ parent,
+                                                                 int *arrived, Scalars *sc, int n, int m, float thetaMacro,
+                                                                 float eps) {
+    __shared__ float dq[kMaxDepth];
     if (sc->error != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->bottom = m;  // buildtree.cl:117
         return;
     }
+    if (threadIdx.x == 0) fill_dq(dq, sc, thetaMacro, eps);
+    __syncthreads();
     const int bottom = sc->bottom;
     const int stride = gridDim.x * blockDim.x;
     for (int first = bottom + blockIdx.x * blockDim.x + threadIdx.x; first <= m; first += stride) {
         int cell = first;
-        // A cell is summarised by whoever reports last among its child cells and its own thread.  `arrived` holds
-        // the number of child cells (maintained by build) in its high half and the reports in its low half, so one
-        // atomic on a small, L2-resident array both reports and tells whether this was the last report.
-        int old = atomicAdd(arrived + (cell - n), 1);
-        if ((old & 0xffff) != (old >> 16)) continue;
-        __threadfence();
+        // A cell is summarised by whoever reports last among its child cells and its own thread.
+        int old = atom_add_acquire(arrived + (cell - n), 1);
+        if ((old & 0xff) != ((old >> 8) & 0xff)) continue;
         for (;;) {
+            const int level = min(old >> 16, kMaxDepth - 1);
             int *row = child + (size_t)(cell - n) * 8;
             const int4 lo = __ldcg(reinterpret_cast<const int4 *>(row)), hi = __ldcg(reinterpret_cast<const int4 *>(row) + 1);
             const int in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -408,46 +456,51 @@ __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__re
                 c[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 cnt[k] = 0;
                 if (out[k] >= n) {
-                    c[k] = __ldcg(node4 + out[k]);
+                    c[k] = __ldcg(cell4 + (out[k] - n));
                     cnt[k] = __ldcg(count + (out[k] - n));
                 } else if (out[k] >= 0) {
-                    c[k] = node4[out[k]];
+                    c[k] = body4[out[k]];
                     cnt[k] = 1;
                 }
             }
             float cm = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
             int bodies = 0;  // summarizetree.cl:98-105,118
             float4 *orow = octet + (size_t)(cell - n) * 8;
-            int *irow = oidx + (size_t)(cell - n) * 8;
+            int2 *mrow = ometa + (size_t)(cell - n) * 8;
+            const int thrBits = __float_as_int(dq[level]);
+            const int bodyThr = __float_as_int(-1.0f);
             int cpos = 0, bpos = ncell;  // the force walk's record: child cells first, then child bodies
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (out[k] < 0) break;
-                bodies += cnt[k];
+                bodies += cnt[k] & kCountMask;
                 cm = __fadd_rn(cm, c[k].w);  // summarizetree.cl:107-110, octant order
                 cx = fmaf(c[k].x, c[k].w, cx);
                 cy = fmaf(c[k].y, c[k].w, cy);
                 cz = fmaf(c[k].z, c[k].w, cz);
                 if (out[k] >= n) {
-                    irow[cpos] = out[k] - n;
+                    mrow[cpos] = make_int2(thrBits, (out[k] - n) | ((cnt[k] >> 28) << 27));
                     orow[cpos++] = c[k];
                 } else {
+                    mrow[bpos] = make_int2(bodyThr, -1);
                     orow[bpos++] = c[k];
                 }
             }
             reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
             reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
-            meta[cell - n] = ncell | ((used - ncell) << 4);  // force walk: #child cells, #child bodies
+            meta[cell - n] = ncell | ((used - ncell) << 4);  // deep walk: #child cells, #child bodies
             const float inv = __frcp_rn(cm);  // summarizetree.cl:161: 1.0f / cellMass, correctly rounded
-            __stcg(node4 + cell, make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
-            __stcg(count + (cell - n), bodies);  // summarizetree.cl:160
-            if (cell == m) break;                // the root
-            // report to the parent; the child that reports last continues with it
+            __stcg(cell4 + (cell - n), make_float4(__fmul_rn(cx, inv), __fmul_rn(cy, inv), __fmul_rn(cz, inv), cm));
+            __stcg(count + (cell - n), bodies | ((used - 1) << 28));  // summarizetree.cl:160 (+ #children for the walk entry)
+            if (cell == m) {  // the root
+                sc->rootEntry = (m - n) | ((used - 1) << 27);
+                break;
+            }
+            // report to the parent; the child that reports last continues with it (summarizetree.cl:170: release
+            // this cell's record, acquire the siblings')
             const int par = parent[cell - n];
-            __threadfence();  // summarizetree.cl:170: this cell's record before the report
-            old = atomicAdd(arrived + (par - n), 1);
-            if ((old & 0xffff) != (old >> 16)) break;  // not the last report: somebody else continues
-            __threadfence();
+            old = atom_add_acq_rel(arrived + (par - n), 1);
+            if ((old & 0xff) != ((old >> 8) & 0xff)) break;  // not the last report: somebody else continues
             cell = par;
         }
     }
@@ -456,10 +509,12 @@ __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(float4 *__re
 // ---- 4. sort ----------------------------------------------------------------------
 // sort.cl: top-down propagation of `start`, bodies written in DFS order.  One
 // thread per cell, descending index (parents first), waits for start >= 0.
+// Launched cooperatively (all CTAs co-resident, or the launch waits): a waiting
+// thread's parent is always being processed by a resident thread.
 constexpr int kSortThreads = 256;
 
 __global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restrict__ child, const int *__restrict__ count,
-                                                            int *start, int *__restrict__ sorted, Scalars *sc, int n, int m) {
+                                                            int *start, int *__restrict__ perm, Scalars *sc, int n, int m) {
     if (sc->error != 0) return;
     const int bottom = sc->bottom;
     const int stride = gridDim.x * blockDim.x;
@@ -479,38 +534,27 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const int *__restric
             if (ch[k] < 0) break;  // compacted
             if (ch[k] >= n) {      // sort.cl:44-56
                 st_relaxed(start + (ch[k] - n), s);
-                s += count[ch[k] - n];
+                s += count[ch[k] - n] & kCountMask;
             } else {               // sort.cl:59-65
-                sorted[s++] = ch[k];
+                perm[s++] = ch[k];
             }
         }
     }
 }
 
-constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 children, 7 stay while the 8th is walked
-
 // ---- 5. force -------------------------------------------------------------------
-// calculateforce.cl: a vote group of VOTE consecutive sorted bodies walks the tree
+// calculateforce.cl: a vote group of 16 consecutive sorted bodies walks the tree
 // together; a cell is used as a point mass only if *all* bodies of the group
 // are far enough (work_group_all, :145), bodies are always used.  The set of
 // (group, node) interactions is exactly the reference's; the order in which a
-// body sums them differs (all children of a popped cell are consumed before its
-// opened children are descended), which moves the fp32 sum by rounding only.
-// The kernel is built around Blackwell's packed fp32 pipe
-// (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot).  The walk is
-// issue-bound, so every lane carries TWO consecutive sorted bodies and a warp
-// carries 64 bodies = 64/VOTE vote groups (lanes 8g..8g+7 are group g for
-// VOTE = 16).  A stack entry is {cell - N, one bit per group that still needs the
-// cell | depth << 1}; a group that accepted a cell is simply absent from the
-// mask of its children.  Per pop one LDG.128 brings the cell's walk record (8
-// children + 8 indices, written by summarise) into a per-warp shared-memory row
-// -- per-child global loads miss L1 on every second child (32-byte sectors) and
-// each miss costs an L2 round trip -- and the children are consumed with
-// broadcast LDS.128: child cells first (7 packed fp32 ops, one ballot; a second
-// ballot and the push only if some body is too near), then child bodies.  (An L1
-// prefetch of pushed cells was measured and dropped: 2 % slower than none.)
-constexpr int kForce2Threads = 128;
-constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
+// body sums them differs, which moves the fp32 sum by rounding only.
+//
+// Both kernels are built around Blackwell's packed fp32 pipe (FADD2 / FMUL2 /
+// FFMA2: two IEEE fp32 operations per issue slot): every lane carries TWO
+// consecutive sorted bodies, a warp 64 bodies = four 16-body vote groups (lanes
+// 8g..8g+7 are group g).  Results go to the tree-order acceleration buffer(s)
+// `dst` (the rank's own and, in a multi-GPU run with peer memory, every other
+// rank's over NVLink: the all-gather is fused into the walk's epilogue).
 
 __device__ __forceinline__ float rsqrt_fast(float x) {
     // r^2 >= EPSILON > 0 is never subnormal: the bare MUFU.RSQ (2 ulp, calculateforce.cl:146 allows rsqrt's 2 ulp)
@@ -531,7 +575,12 @@ __device__ __forceinline__ void sts_v4(unsigned a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+// global -> shared without a register round trip (LDGSTS)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ const char *lane_address(const char *base, int rel, int stride) {
     unsigned long long a;
@@ -549,39 +598,221 @@ __device__ __forceinline__ void force_accumulate(float2 dx, float2 dy, float2 dz
     az = __ffma2_rn(dz, f, az);
 }
 
-// Destinations of a slice's accelerations: the rank's own sorted-order buffer and, in a multi-GPU run with
-// peer memory, the same buffer of every other rank mapped over NVLink (CUDA IPC): the walk's epilogue stores
-// straight into all of them, so the all-gather is fused into the force kernel and overlaps the walk.
+#define BH_DIST(c, S)                                                                                                  \
+    const float2 dx##S = __fadd2_rn(make_float2((c).x, (c).x), npx); /* c - p, exactly */                              \
+    const float2 dy##S = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                   \
+    const float2 dz##S = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                   \
+    const float2 r2##S = __fadd2_rn(__ffma2_rn(dz##S, dz##S, __ffma2_rn(dy##S, dy##S, __fmul2_rn(dx##S, dx##S))), eps2); /* :138-143 */
+
+// Destinations of a slice's accelerations: the rank's own tree-order buffer and, in a multi-GPU run with
+// peer memory, the same buffer of every other rank mapped over NVLink (CUDA IPC).  `phaseStride` (float4s)
+// selects the half used in this step (step & 1): peers may already store the next step's slices while this
+// step's are still being read.  0 = single buffer.
 constexpr int kMaxPeers = 16;
 struct PeerBuffers {
     float4 *buf[kMaxPeers];
     int count;
+    unsigned phaseStride;
 };
 
-template <int VOTE, bool SLICE, bool COUNT>
-__global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ octet,
-                                                                 const int *__restrict__ oidx, const int *__restrict__ meta,
-                                                                 const int *__restrict__ sorted, float4 *__restrict__ velacc,
-                                                                 const PeerBuffers dst, Scalars *sc, int n, int m,
-                                                                 int first, int cnt, float thetaMacro, float eps, float dt) {
+// ---- 5a. the walk: one private work list per vote group ---------------------------------------------------------
+// Every vote group (8 lanes) keeps, in shared memory, a stack of cells it has decided to open and a LIFO of
+// child records waiting to be tested.  A warp-wide step tests ONE queued child per group -- four different
+// children, each against its own group's 16 bodies (LDS.128 with one address per quarter warp) -- so no lane
+// ever works on a node its group does not need (a shared walk of the four groups' union costs ~25 % more
+// child tests), and the per-cell bookkeeping of a stack walk (pop, row fetch, loop control: a third of the
+// issue slots of a pop-per-cell design) is paid once per ~25 children: when a group's queue runs low its
+// lanes pop up to eight cells at once (one per lane; the number of children is part of the stack entry, so
+// the space is assigned by an 8-lane prefix sum without touching memory) and LDGSTS copies the children's
+// records {x,y,z,m} + {threshold, entry} from the cells' walk records straight into the queue.
+// Per child: LDS.128 + LDS.64, 7 packed fp32 (distance), 2 FSETP + VOTE + LOP3 (the group's vote, :145),
+// 2 MUFU.RSQ, 6 packed fp32 (the interaction, zero mass if the group opens the cell), predicated push.
+// If a group's cell stack cannot take another batch (trees deeper than ~25 levels at theta = 0.5) the kernel
+// raises sc->deep and deep_walk_kernel, launched right behind it, redoes the stage with its 64-level stack.
+constexpr int kWalkThreads = 128;
+constexpr int kWalkBodies = 2 * kWalkThreads;  // per CTA
+constexpr int kWalkBatch = 6;    // children tested per group between two looks at the queue
+constexpr int kWalkQCap = 32;    // queued children per group
+constexpr int kWalkSCap = 160;   // stacked cells per group
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
+                                                            const int2 *__restrict__ ometa, const int *__restrict__ perm,
+                                                            const PeerBuffers dst, Scalars *sc, int n, int first, int cnt,
+                                                            float eps, int forceDeep) {
+    constexpr int kWarps = kWalkThreads / 32;
+    constexpr int kSlots = kWalkBatch + kWalkQCap;  // the lowest kWalkBatch slots hold zero-mass dummies
+    __shared__ int stk[kWarps][4][kWalkSCap];
+    __shared__ float4 qrec[kWarps][4][kSlots];
+    __shared__ int2 qmeta[kWarps][4][kSlots];
+    if (sc->error != 0) return;
+    if (sc->maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
+        return;
+    }
+    if (forceDeep) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->deep = 1;
+        return;
+    }
+    if (*reinterpret_cast<volatile int *>(&sc->deep) != 0) return;  // another CTA already gave up: the stage is redone anyway
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, j = lane & 7;
+    const int end = first + cnt;
+    const int base = first + (blockIdx.x * kWarps + warp) * 64;
+    // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
+    const int k0 = base + 2 * lane;
+    const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
+    unsigned gm = 0xffu << (8 * g);             // lanes of my group
+    asm volatile("" : "+r"(gm));                // keep it in a register (ptxas would rematerialise it per vote)
+    // a slot past the end borrows the position of the group's first body: its vote then equals that body's
+    const int kg = base + 16 * g;
+    const int s0 = (nact > 0) ? k0 : max(0, min(kg, end - 1)), s1 = (nact > 1) ? k0 + 1 : s0;
+    const float4 p0 = body4[perm ? perm[s0] : s0], p1 = body4[perm ? perm[s1] : s1];  // perm == nullptr: bodies lie in tree order
+    const float2 npx = make_float2(-p0.x, -p1.x), npy = make_float2(-p0.y, -p1.y), npz = make_float2(-p0.z, -p1.z);
+    const float2 eps2 = make_float2(eps, eps);
+    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+    unsigned long long nInter = 0, nOpen = 0;
+    // shared memory through 32-bit shared-window addresses kept in registers
+    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(&stk[warp][g][0]);
+    const unsigned stkLimit = stkBase + 4u * (kWalkSCap - kWalkBatch);  // a batch pushes at most kWalkBatch cells
+    const unsigned qBase = (unsigned)__cvta_generic_to_shared(&qrec[warp][g][kWalkBatch]);
+    const unsigned mBase = (unsigned)__cvta_generic_to_shared(&qmeta[warp][g][kWalkBatch]);
+    if (j < kWalkBatch) {  // dummies: zero mass, always accepted, never counted
+        qrec[warp][g][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qmeta[warp][g][j] = make_int2(__float_as_int(-1.0f), -2);
+    }
+    unsigned stkTop = stkBase, qTop = qBase, mTop = mBase;  // one past the top entry; the same in all lanes of a group
+    const bool groupActive = (__ballot_sync(kFull, nact > 0) & gm) != 0u;
+    if (groupActive) {
+        sts_s32(stkTop, sc->rootEntry);
+        stkTop += 4;
+    }
+    __syncwarp();
+    for (;;) {
+        const bool low = qTop < qBase + 16u * kWalkBatch;  // fewer than a batch of real children queued
+        const bool need = low && stkTop != stkBase;
+        if (__any_sync(kFull, need)) {
+            // ---- refill: lane j of a group in need pops the j-th cell from the top of its stack ------------------
+            const int avail = (int)(stkTop - stkBase) >> 2;
+            int e = 0, c = 0;
+            if (need && j < avail) {
+                e = lds_s32(stkTop - 4u * (unsigned)(j + 1));
+                c = ((e >> 27) & 7) + 1;  // children of my cell
+            }
+            int incl = c;  // inclusive prefix sum within the group
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o, 8);
+                if (j >= o) incl += v;
+            }
+            const int freeSlots = kWalkQCap - ((int)(qTop - qBase) >> 4);
+            const bool take = c > 0 && incl <= freeSlots;  // true for a prefix of the lanes (incl grows with j)
+            const int taken = __popc(__ballot_sync(kFull, take) & gm);
+            const int total = __shfl_sync(kFull, incl, max(taken - 1, 0), 8);  // children of the cells taken
+            if (take) {
+                const int rel = e & kEntryMask;
+                const float4 *src = octet + (size_t)rel * 8;
+                const int2 *msrc = ometa + (size_t)rel * 8;
+                const unsigned d = qTop + 16u * (unsigned)(incl - c), md = mTop + 8u * (unsigned)(incl - c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < c) {
+                        cp_async16(d + 16u * k, src + k);
+                        cp_async8(md + 8u * k, msrc + k);
+                    }
+            }
+            if (taken > 0) {
+                stkTop -= 4u * (unsigned)taken;
+                qTop += 16u * (unsigned)total;
+                mTop += 8u * (unsigned)total;
+            }
+            cp_async_wait_all();
+            __syncwarp();
+        } else if (__all_sync(kFull, qTop == qBase)) {
+            break;  // every group: nothing queued, nothing stacked
+        }
+        if (__any_sync(kFull, stkTop > stkLimit)) {  // no room for the pushes of another batch: leave it to the deep kernel
+            if (lane == 0) sc->deep = 1;
+            return;
+        }
+        // ---- one batch: the top kWalkBatch queued children of every group (dummies below a short queue) ----------
+#pragma unroll
+        for (int i = 1; i <= kWalkBatch; ++i) {
+            const float4 c = lds_v4(qTop - 16u * i);
+            int thrBits, ent;
+            lds_v2(mTop - 8u * i, thrBits, ent);
+            const float thr = __int_as_float(thrBits);
+            BH_DIST(c, 0)
+            const bool far = !(r20.x < thr) && !(r20.y < thr);  // r^2 >= dq (a NaN never opens: no entry of a body is ever pushed)
+            const unsigned nearMask = __ballot_sync(kFull, !far);
+            const bool open = (nearMask & gm) != 0u;  // :145 work_group_all failed: my group opens the cell
+            force_accumulate(dx0, dy0, dz0, r20, open ? 0.0f : c.w, ax, ay, az);
+            if (open) {  // all lanes of the group store the same entry to the same address
+                sts_s32(stkTop, ent);
+                stkTop += 4;
+            }
+            if (COUNT) {
+                if (open) nOpen += nact;
+                else if (ent != -2) nInter += nact;
+            }
+        }
+        qTop = max(qTop - 16u * kWalkBatch, qBase);
+        mTop = max(mTop - 8u * kWalkBatch, mBase);
+        __syncwarp();  // pushes of this batch before the next refill reads them
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            nInter += __shfl_xor_sync(kFull, nInter, o);
+            nOpen += __shfl_xor_sync(kFull, nOpen, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sc->interactions, nInter);
+            atomicAdd(&sc->opens, nOpen);
+        }
+    }
+    const size_t phase = (size_t)(sc->step & 1) * dst.phaseStride;
+    if (nact == 2) {
+        const float4 a0 = make_float4(ax.x, ay.x, az.x, 0.0f), a1 = make_float4(ax.y, ay.y, az.y, 0.0f);
+        for (int r = 0; r < dst.count; ++r) {  // own buffer, then the peers' (NVLink stores)
+            float4 *out = dst.buf[r] + phase + k0;
+            out[0] = a0;
+            out[1] = a1;
+        }
+    } else if (nact == 1) {
+        const float4 a0 = make_float4(ax.x, ay.x, az.x, 0.0f);
+        for (int r = 0; r < dst.count; ++r) dst.buf[r][phase + k0] = a0;
+    }
+}
+
+// ---- 5b. the deep walk: one shared stack per warp, 64 levels ---------------------------------------------------
+// Round 1's walk, kept as the fallback for trees too deep for walk_kernel's shared-memory stacks (sc->deep)
+// and for the non-reference 32-wide vote.  A stack entry is {cell - N, one bit per group that still needs the
+// cell | depth << 1}; a group that accepted a cell is simply absent from the mask of its children; the warp
+// walks the union of its groups' trees.  Per pop one LDG.128 per lane brings the cell's walk record (8
+// children + 8 {threshold, entry} pairs) into a per-warp shared-memory row; the children are consumed with
+// broadcast LDS.128, child cells first and in pairs (two independent distance chains, one VOTE.ALL for both
+// when every body of the warp is far from both).
+constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 children, 7 stay while the 8th is walked
+constexpr int kForce2Threads = 128;
+constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
+
+template <int VOTE, bool ONLY_IF_DEEP, bool COUNT>
+__global__ void __launch_bounds__(kForce2Threads) deep_walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
+                                                                    const int2 *__restrict__ ometa, const int *__restrict__ meta,
+                                                                    const int *__restrict__ perm, const PeerBuffers dst, Scalars *sc,
+                                                                    int n, int m, int first, int cnt, float thetaMacro, float eps) {
     __shared__ float dq[kMaxDepth];
     __shared__ int2 stack[kForce2Threads / 32][kStackCap];  // {cell - N, group bits | depth << 1}
-    __shared__ float4 stage[kForce2Threads / 32][10];       // the popped cell's walk record: 8 children, 8 indices
+    __shared__ float4 stage[kForce2Threads / 32][12];       // the popped cell's walk record: 8 children, 8 {threshold, entry}
     if (sc->error != 0) return;
+    if (ONLY_IF_DEEP && sc->deep == 0) return;
     const int maxDepth = sc->maxDepth;
     if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
         return;
     }
-    if (threadIdx.x == 0) {  // calculateforce.cl:52-67
-        const float radius = sc->radius;
-        float v = __fmul_rn(radius, radius);
-        if (thetaMacro > 0.0f) v = __fdiv_rn(v, thetaMacro);
-        for (int i = 0; i < maxDepth; ++i) {
-            dq[i] = __fadd_rn(v, eps);
-            v = __fmul_rn(0.25f, v);
-        }
-    }
+    if (threadIdx.x == 0) fill_dq(dq, sc, thetaMacro, eps);
     __syncthreads();
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kLanesPerGroup = VOTE / 2;  // two bodies per lane
@@ -589,7 +820,19 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     constexpr unsigned kSpread = (kLanesPerGroup == 8) ? 0x01010101u : (kLanesPerGroup == 16) ? 0x00010001u : 1u;  // first lane of every group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int end = first + cnt;
-    const int base = first + (blockIdx.x * (kForce2Threads / 32) + warp) * 64;
+    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(stack[warp]);
+    unsigned rowBase = (unsigned)__cvta_generic_to_shared(stage[warp]);
+    unsigned dqBase = (unsigned)__cvta_generic_to_shared(dq);
+    unsigned rowLane = rowBase + 16u * (unsigned)lane;
+    // lanes 0-7 fetch the 8 child records, lanes 8-11 the 8 {threshold, entry} pairs
+    const char *laneBase = lane < 8 ? reinterpret_cast<const char *>(octet + lane)
+                                    : reinterpret_cast<const char *>(ometa) + 16 * ((lane - 8) & 3);
+    int laneStride = lane < 8 ? 128 : 64;
+    asm volatile("" : "+r"(rowBase), "+r"(dqBase), "+r"(rowLane), "+r"(laneStride));  // keep them in registers
+    const size_t phase = (size_t)(sc->step & 1) * dst.phaseStride;
+    const int chunks = (cnt + kForce2Bodies - 1) / kForce2Bodies;
+    for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const int base = first + (chunk * (kForce2Threads / 32) + warp) * 64;
     // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
     const int k0 = base + 2 * lane;
     const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
@@ -600,23 +843,11 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
     // a slot past the end borrows the position of the group's first body: its vote then equals that body's
     const int kg = base + 2 * gfirst;
     const int s0 = (nact > 0) ? k0 : max(0, min(kg, end - 1)), s1 = (nact > 1) ? k0 + 1 : s0;
-    const int b0 = sorted[s0], b1 = sorted[s1];
-    const float4 p0 = node4[b0], p1 = node4[b1];
+    const float4 p0 = body4[perm ? perm[s0] : s0], p1 = body4[perm ? perm[s1] : s1];
     const float2 npx = make_float2(-p0.x, -p1.x), npy = make_float2(-p0.y, -p1.y), npz = make_float2(-p0.z, -p1.z);
     const float2 eps2 = make_float2(eps, eps);
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
     unsigned long long nInter = 0, nOpen = 0;
-    // Shared memory is addressed through 32-bit shared-window addresses kept in registers (ptxas otherwise
-    // rebuilds the window base from SR_CgaCtaId on every pop).
-    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(stack[warp]);
-    unsigned rowBase = (unsigned)__cvta_generic_to_shared(stage[warp]);
-    unsigned dqBase = (unsigned)__cvta_generic_to_shared(dq);
-    unsigned rowLane = rowBase + 16u * (unsigned)lane;
-    // lanes 0-7 fetch the 8 child records, lanes 8-9 the 8 child indices
-    const char *laneBase = lane < 8 ? reinterpret_cast<const char *>(octet + lane)
-                                    : reinterpret_cast<const char *>(oidx) + 16 * ((lane - 8) & 1);
-    int laneStride = lane < 8 ? 128 : 32;
-    asm volatile("" : "+r"(rowBase), "+r"(dqBase), "+r"(rowLane), "+r"(laneStride));  // keep them in registers
     // groups with at least one existing body take part in the walk
     const unsigned lanesActive = __ballot_sync(kFull, nact > 0);
     unsigned startBits = 0;
@@ -633,7 +864,7 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         int rel, ey;
         lds_v2(sp, rel, ey);
         __syncwarp();  // every lane has read the entry and is done with the previous row
-        if (lane < 10) sts_v4(rowLane, __ldg(reinterpret_cast<const float4 *>(lane_address(laneBase, rel, laneStride))));
+        if (lane < 12) sts_v4(rowLane, __ldg(reinterpret_cast<const float4 *>(lane_address(laneBase, rel, laneStride))));
         // REDUX puts the (warp-uniform) word into a uniform register: ptxas then knows that the
         // branches on it are uniform and emits no divergence guards around the votes
         const int mt = __reduce_or_sync(kFull, __ldg(meta + rel));
@@ -645,11 +876,6 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         const float mscale = mine ? 1.0f : 0.0f;
         const int ncell = mt & 15, nbody = mt >> 4;
         __syncwarp();
-#define BH_DIST(c, S)                                                                                                  \
-    const float2 dx##S = __fadd2_rn(make_float2((c).x, (c).x), npx); /* c - p, exactly */                              \
-    const float2 dy##S = __fadd2_rn(make_float2((c).y, (c).y), npy);                                                   \
-    const float2 dz##S = __fadd2_rn(make_float2((c).z, (c).z), npz);                                                   \
-    const float2 r2##S = __fadd2_rn(__ffma2_rn(dz##S, dz##S, __ffma2_rn(dy##S, dy##S, __fmul2_rn(dx##S, dx##S))), eps2); /* :138-143 */
         // one child cell whose vote was not unanimous (or that was not tested as part of a pair)
 #define BH_CELL_VOTE(c, S, far, j)                                                                                     \
     if (__all_sync(kFull, far)) { /* far enough for every body of the warp: every group that is here uses it */      \
@@ -659,7 +885,7 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
         const unsigned near = __ballot_sync(kFull, !(far));                                                            \
         const unsigned open = __ballot_sync(kFull, (near & gmMine) != 0u);                                             \
         if (open) { /* :154-163 */                                                                                     \
-            const int ch = lds_s32(rowBase + 128u + 4u * (j));                                                         \
+            const int ch = lds_s32(rowBase + 132u + 8u * (j)) & kEntryMask;                                            \
             sts_v2(sp, ch, (int)((open & kSpread) | (unsigned)dnext));                                                 \
             sp += 8;                                                                                                   \
         }                                                                                                              \
@@ -670,9 +896,6 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             if (COUNT && use) nInter += nact;                                                                          \
         }                                                                                                              \
     }
-        // Child cells come first and are taken two at a time: two independent distance chains per lane hide the
-        // fp32 latency (dependency waits were the top stall), and the common case -- both cells far from every
-        // body of the warp (the group vote of :145 is then unanimous in all groups) -- costs one VOTE for two.
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
             if (j + 2 > ncell) break;
@@ -715,7 +938,6 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             if (COUNT && mine) nInter += nact;
         }
 #undef BH_CELL_VOTE
-#undef BH_DIST
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -727,124 +949,223 @@ __global__ void __launch_bounds__(kForce2Threads) force2_kernel(const float4 *__
             atomicAdd(&sc->opens, nOpen);
         }
     }
-    const bool corr = sc->step > 0;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         if (t >= nact) break;
-        const int body = t ? b1 : b0;
-        const float fx = t ? ax.y : ax.x, fy = t ? ay.y : ay.x, fz = t ? az.y : az.x;
-        if (SLICE) {
-            const float4 a = make_float4(fx, fy, fz, 0.0f);
-            for (int r = 0; r < dst.count; ++r) dst.buf[r][k0 + t] = a;  // own buffer, then the peers' (NVLink stores)
-        } else {
-            if (corr) {  // calculateforce.cl:174-179
-                float4 v = velacc[2 * (size_t)body];
-                const float4 a0 = velacc[2 * (size_t)body + 1];
-                v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(fx, a0.x), dt), 0.5f));
-                v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(fy, a0.y), dt), 0.5f));
-                v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(fz, a0.z), dt), 0.5f));
-                velacc[2 * (size_t)body] = v;
-            }
-            velacc[2 * (size_t)body + 1] = make_float4(fx, fy, fz, 0.0f);  // :183-185
-        }
+        const float4 a = make_float4(t ? ax.y : ax.x, t ? ay.y : ay.x, t ? az.y : az.x, 0.0f);
+        for (int r = 0; r < dst.count; ++r) dst.buf[r][phase + k0 + t] = a;  // own buffer, then the peers' (NVLink stores)
+    }
+    __syncwarp();
     }
 }
+#undef BH_DIST
 
-// Multi-GPU: velocity correction + acc store from the all-gathered sorted-order
-// accelerations (calculateforce.cl:174-185 for every body).
-__global__ void __launch_bounds__(256) apply_acc_kernel(const float4 *__restrict__ accSorted, const int *__restrict__ sorted,
-                                                        float4 *__restrict__ velacc, const Scalars *__restrict__ sc, int n,
-                                                        float dt) {
+// ---- 6. finish: velocity correction + integrate + physical reordering --------------------------------------------
+// calculateforce.cl:174-185 (vel += (a - a_old) * dt * 0.5 for step > 0; acc = a) and integrate.cl:27-43, for the
+// body in slot perm[k], which then moves to slot k of the other buffers: after the step the bodies lie in this
+// step's tree order, which is next step's insertion order (build), gather order (summarise) and walk order.
+// APPLY = false: integrate only (the stage-by-stage API has applied the accelerations in calculate_force);
+// PERMUTE = false: bodies stay where they are (bh_set_insertion_order(0), or no fresh sort).
+// vpos/vvel (optional) = copyvertices.cl:14-17 fused: float4 {x,y,z,1} / {vx,vy,vz,1} in the host's numbering.
+template <bool APPLY, bool PERMUTE>
+__global__ void __launch_bounds__(256) finish_kernel(const float4 *bodyIn, const float4 *vaIn, float4 *bodyOut, float4 *vaOut,
+                                                     const float4 *__restrict__ acc, unsigned phaseStride,
+                                                     const int *__restrict__ perm, const Scalars *__restrict__ sc, int n, float dt,
+                                                     float4 *__restrict__ vpos, float4 *__restrict__ vvel) {
     if (sc->error != 0) return;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const int body = sorted[k];
-    const float4 a = accSorted[k];
-    if (sc->step > 0) {
-        float4 v = velacc[2 * (size_t)body];
-        const float4 a0 = velacc[2 * (size_t)body + 1];
-        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(a.x, a0.x), dt), 0.5f));
-        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(a.y, a0.y), dt), 0.5f));
-        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(a.z, a0.z), dt), 0.5f));
-        velacc[2 * (size_t)body] = v;
+    const int src = ((APPLY || PERMUTE) && perm) ? perm[k] : k;  // perm == nullptr: bodies already lie in tree order
+    const int dstSlot = PERMUTE ? k : src;
+    float4 p = bodyIn[src];
+    float4 v = vaIn[2 * (size_t)src];
+    float4 a = vaIn[2 * (size_t)src + 1];
+    if (APPLY) {
+        const int step = sc->step;
+        const float4 an = acc[(size_t)(step & 1) * phaseStride + k];
+        if (step > 0) {  // calculateforce.cl:174-179
+            v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(an.x, a.x), dt), 0.5f));
+            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(an.y, a.y), dt), 0.5f));
+            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(an.z, a.z), dt), 0.5f));
+        }
+        a = make_float4(an.x, an.y, an.z, 0.0f);  // :183-185
     }
-    velacc[2 * (size_t)body + 1] = make_float4(a.x, a.y, a.z, 0.0f);
-}
-
-// ---- 6. integrate ---------------------------------------------------------------
-// integrate.cl:27-43
-__global__ void __launch_bounds__(256) integrate_kernel(float4 *__restrict__ node4, float4 *__restrict__ velacc,
-                                                        const Scalars *__restrict__ sc, int n, float dt) {
-    if (sc->error != 0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = node4[i];
-    float4 v = velacc[2 * (size_t)i];
-    const float4 a = velacc[2 * (size_t)i + 1];
+    // integrate.cl:29-43
     const float dvx = __fmul_rn(__fmul_rn(a.x, dt), 0.5f);
     const float dvy = __fmul_rn(__fmul_rn(a.y, dt), 0.5f);
     const float dvz = __fmul_rn(__fmul_rn(a.z, dt), 0.5f);
     v.x = __fadd_rn(v.x, dvx); v.y = __fadd_rn(v.y, dvy); v.z = __fadd_rn(v.z, dvz);
     p.x = fmaf(v.x, dt, p.x); p.y = fmaf(v.y, dt, p.y); p.z = fmaf(v.z, dt, p.z);
     v.x = __fadd_rn(v.x, dvx); v.y = __fadd_rn(v.y, dvy); v.z = __fadd_rn(v.z, dvz);
-    node4[i] = p;
-    velacc[2 * (size_t)i] = v;
+    bodyOut[dstSlot] = p;
+    vaOut[2 * (size_t)dstSlot] = v;  // v.w = origId travels with the body
+    if (APPLY || PERMUTE) vaOut[2 * (size_t)dstSlot + 1] = a;
+    if (vpos || vvel) {
+        const int id = __float_as_int(v.w);
+        if (vpos) vpos[id] = make_float4(p.x, p.y, p.z, 1.0f);
+        if (vvel) vvel[id] = make_float4(v.x, v.y, v.z, 1.0f);
+    }
+}
+
+// calculateforce.cl:174-185 alone (bh_calculate_force of the stage-by-stage API): in place
+__global__ void __launch_bounds__(256) apply_acc_kernel(const float4 *__restrict__ acc, unsigned phaseStride,
+                                                        const int *__restrict__ perm, float4 *__restrict__ velacc,
+                                                        const Scalars *__restrict__ sc, int n, float dt) {
+    if (sc->error != 0) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int slot = perm ? perm[k] : k;
+    const int step = sc->step;
+    const float4 a = acc[(size_t)(step & 1) * phaseStride + k];
+    if (step > 0) {
+        float4 v = velacc[2 * (size_t)slot];
+        const float4 a0 = velacc[2 * (size_t)slot + 1];
+        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fsub_rn(a.x, a0.x), dt), 0.5f));
+        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fsub_rn(a.y, a0.y), dt), 0.5f));
+        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fsub_rn(a.z, a0.z), dt), 0.5f));
+        velacc[2 * (size_t)slot] = v;
+    }
+    velacc[2 * (size_t)slot + 1] = make_float4(a.x, a.y, a.z, 0.0f);
+}
+
+// ---- multi-GPU: device-side barrier over peer memory ---------------------------------------------------------------
+// Every rank owns `flags[kMaxPeers]` (unsigned long long) in its peer-mapped allocation.  barrier_kernel (one
+// warp) bumps the rank's own sequence number, release-stores it at system scope into slot `rank` of every peer's
+// flags, and waits until every peer's number has arrived in its own flags.  Stream order puts the walk's peer
+// stores before the barrier's release and the barrier's acquire before finish_kernel's loads.
+struct PeerFlags {
+    unsigned long long *flags[kMaxPeers];  // flags[r] = rank r's flag array (own = local pointer)
+    int count, rank;
+};
+
+__global__ void barrier_kernel(const PeerFlags pf, unsigned long long *seq, Scalars *sc, long long timeoutCycles) {
+    const int r = threadIdx.x;
+    unsigned long long s = *seq + 1;
+    __syncwarp();
+    if (r == 0) *seq = s;
+    if (r >= pf.count || r == pf.rank) return;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf.flags[r] + pf.rank), "l"(s) : "memory");
+    const unsigned long long *mine = pf.flags[pf.rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= s) break;
+        if (clock64() - t0 > timeoutCycles) {  // a peer died or fell out of step: report instead of hanging
+            atomicCAS(&sc->error, 0, 3);
+            break;
+        }
+        __nanosleep(64);
+    }
 }
 
 // ---- host-boundary helpers: pack uploads, export logical buffers -------------------
 __global__ void pack_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
                             const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
-                            const float *__restrict__ mass, float4 *__restrict__ node4, float4 *__restrict__ velacc,
-                            int *__restrict__ sorted, int n) {
+                            const float *__restrict__ mass, float4 *__restrict__ body4, float4 *__restrict__ velacc,
+                            int *__restrict__ perm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    node4[i] = make_float4(x[i], y[i], z[i], mass[i]);
-    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+    body4[i] = make_float4(x[i], y[i], z[i], mass[i]);
+    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], __int_as_float(i));
     velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    sorted[i] = 0;
+    perm[i] = 0;
 }
 
-// comp 0..3 of node4 for i < len
-__global__ void export_node_kernel(const float4 *__restrict__ node4, int comp, float *__restrict__ out, long long len) {
+// Logical float buffers (GPUBH:198-205): bodies 0..n-1 in the host's numbering, cells n..m; `which`: 0-2 pos,
+// 3-5 vel, 6-8 acc, 9 mass.  vel/acc are zero beyond the bodies (the reference never writes there).
+__global__ void export_float_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc,
+                                    const float4 *__restrict__ cell4, int which, float *__restrict__ out, int n, long long len) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    const float4 v = node4[i];
-    out[i] = comp == 0 ? v.x : comp == 1 ? v.y : comp == 2 ? v.z : v.w;
-}
-
-// which = 0 (vel) or 1 (acc); zeros beyond the bodies (the reference never writes there)
-__global__ void export_velacc_kernel(const float4 *__restrict__ velacc, int which, int comp, float *__restrict__ out,
-                                     int n, long long len) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    float r = 0.0f;
-    if (i < n) {
-        const float4 v = velacc[2 * (size_t)i + which];
-        r = comp == 0 ? v.x : comp == 1 ? v.y : v.z;
+    if (i >= len && i >= n) return;
+    if (i < n) {  // slot i: scatter to the host's index
+        const float4 v0 = velacc[2 * (size_t)i];
+        const int id = __float_as_int(v0.w);
+        if (id < len) {
+            float r;
+            if (which < 3 || which == 9) {
+                const float4 p = body4[i];
+                r = which == 0 ? p.x : which == 1 ? p.y : which == 2 ? p.z : p.w;
+            } else if (which < 6) {
+                r = which == 3 ? v0.x : which == 4 ? v0.y : v0.z;
+            } else {
+                const float4 a = velacc[2 * (size_t)i + 1];
+                r = which == 6 ? a.x : which == 7 ? a.y : a.z;
+            }
+            out[id] = r;
+        }
     }
-    out[i] = r;
+    if (i >= n && i < len) {
+        float r = 0.0f;
+        if (which < 3 || which == 9) {
+            const float4 c = cell4[i - n];
+            r = which == 0 ? c.x : which == 1 ? c.y : which == 2 ? c.z : c.w;
+        }
+        out[i] = r;
+    }
 }
 
-// logical int arrays that exist only for cells: zeros for the first `skip` entries
-__global__ void export_shifted_kernel(const int *__restrict__ src, long long skip, int *__restrict__ out, long long len) {
+// logical int arrays that exist only for cells: zeros for the first n entries; mask = bits to keep
+__global__ void export_shifted_kernel(const int *__restrict__ src, long long skip, int mask, int *__restrict__ out, long long len) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= len) return;
-    out[i] = i < skip ? 0 : src[i - skip];
+    int v = 0;
+    if (i >= skip) {
+        v = src[i - skip];
+        if (v >= 0) v &= mask;
+    }
+    out[i] = v;
 }
 
-// copyvertices.cl:14-17
-__global__ void copy_vertices_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ velacc,
+// child[8(M+1)]: zeros for the body rows; body slots translated to the host's numbering through the origIds of the
+// buffers the tree was built from
+__global__ void export_child_kernel(const int *__restrict__ child, const float4 *__restrict__ velaccTree, int n,
+                                    int *__restrict__ out, long long len) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    int v = 0;
+    if (i >= 8ll * n) {
+        v = child[i - 8ll * n];
+        if (v >= 0 && v < n) v = __float_as_int(velaccTree[2 * (size_t)v].w);
+    }
+    out[i] = v;
+}
+
+// sorted[M+1]: pending = the sort's permutation has not been applied yet: origId[perm[k]]; else the bodies lie in
+// tree order: origId[k].  Zeros beyond the bodies.
+__global__ void export_sorted_kernel(const int *__restrict__ perm, const float4 *__restrict__ velacc, int pending, int n,
+                                     int *__restrict__ out, long long len) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    int v = 0;
+    if (i < n) v = __float_as_int(velacc[2 * (size_t)(pending ? perm[i] : (int)i)].w);
+    out[i] = v;
+}
+
+// copyvertices.cl:14-17, host numbering
+__global__ void copy_vertices_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc,
                                      float4 *__restrict__ pos, float4 *__restrict__ vel, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float4 v = velacc[2 * (size_t)i];
+    const int id = __float_as_int(v.w);
     if (pos) {
-        const float4 p = node4[i];
-        pos[i] = make_float4(p.x, p.y, p.z, 1.0f);
+        const float4 p = body4[i];
+        pos[id] = make_float4(p.x, p.y, p.z, 1.0f);
     }
-    if (vel) {
-        const float4 v = velacc[2 * (size_t)i];
-        vel[i] = make_float4(v.x, v.y, v.z, 1.0f);
-    }
+    if (vel) vel[id] = make_float4(v.x, v.y, v.z, 1.0f);
+}
+
+// SoA state dump in the host's numbering (bh_write_universe_file): out = 7 arrays of n floats
+__global__ void export_universe_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc, float *__restrict__ out,
+                                       int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = body4[i], v = velacc[2 * (size_t)i];
+    const size_t id = (size_t)__float_as_int(v.w), N = (size_t)n;
+    out[id] = p.x; out[N + id] = p.y; out[2 * N + id] = p.z;
+    out[3 * N + id] = v.x; out[4 * N + id] = v.y; out[5 * N + id] = v.z;
+    out[6 * N + id] = p.w;
 }
 
 // ---- seeded universe generators on the device (ch.fhnw.woipv.nbody.simulation.universe.*) -----------------------
@@ -855,8 +1176,8 @@ __global__ void copy_vertices_kernel(const float4 *__restrict__ node4, const flo
 // kind 2: RotatingDiskGalaxyGenerator.java:17-43    disk of radius p0, velocity multiplier p1, body 0 = centre mass p2
 __device__ __forceinline__ double philox_uniform(curandStatePhilox4_32_10_t *st) { return 1.0 - curand_uniform_double(st); }  // [0,1)
 
-__global__ void __launch_bounds__(256) generate_kernel(float4 *__restrict__ node4, float4 *__restrict__ velacc,
-                                                       int *__restrict__ sorted, int n, int kind, unsigned long long seed,
+__global__ void __launch_bounds__(256) generate_kernel(float4 *__restrict__ body4, float4 *__restrict__ velacc,
+                                                       int *__restrict__ perm, int n, int kind, unsigned long long seed,
                                                        float p0, float p1, float p2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -901,19 +1222,19 @@ __global__ void __launch_bounds__(256) generate_kernel(float4 *__restrict__ node
             vx = y * v0; vy = -x * v0;
         }
     }
-    node4[i] = make_float4(x, y, z, mass);
-    velacc[2 * (size_t)i] = make_float4(vx, vy, vz, 0.0f);
+    body4[i] = make_float4(x, y, z, mass);
+    velacc[2 * (size_t)i] = make_float4(vx, vy, vz, __int_as_float(i));
     velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    sorted[i] = 0;
+    perm[i] = 0;
 }
 
 // ---- diagnostics (GPUBH:305-365 printEnergy / printImpulse, on the device) ---------------------------
 // out[0] = sum 1/2 m v^2, out[1..3] = sum m v, out[4] = sum m; double accumulation.
-__global__ void __launch_bounds__(256) kinetic_kernel(const float4 *__restrict__ node4, const float4 *__restrict__ velacc,
+__global__ void __launch_bounds__(256) kinetic_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc,
                                                       double *__restrict__ out, int n) {
     double e = 0.0, px = 0.0, py = 0.0, pz = 0.0, ms = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float m = node4[i].w;
+        const float m = body4[i].w;
         const float4 v = velacc[2 * (size_t)i];
         e += 0.5 * m * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z);
         px += (double)m * v.x; py += (double)m * v.y; pz += (double)m * v.z; ms += m;
@@ -932,15 +1253,15 @@ __global__ void __launch_bounds__(256) kinetic_kernel(const float4 *__restrict__
 // (not the reference's unsoftened, doubled printEnergy term).  Direct sum, j-tiles staged through shared memory,
 // fp32 pair terms, per-tile fp32 partial sums folded into double.
 constexpr int kPotTile = 256;
-__global__ void __launch_bounds__(kPotTile) potential_kernel(const float4 *__restrict__ node4, double *__restrict__ out, int n,
+__global__ void __launch_bounds__(kPotTile) potential_kernel(const float4 *__restrict__ body4, double *__restrict__ out, int n,
                                                              float eps) {
     __shared__ float4 tile[kPotTile];
     const int i = blockIdx.x * kPotTile + threadIdx.x;
-    const float4 pi = node4[min(i, n - 1)];
+    const float4 pi = body4[min(i, n - 1)];
     double phi = 0.0;
     for (int j0 = 0; j0 < n; j0 += kPotTile) {
         const int j = j0 + threadIdx.x;
-        tile[threadIdx.x] = j < n ? node4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        tile[threadIdx.x] = j < n ? body4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         float part = 0.0f;
 #pragma unroll 8

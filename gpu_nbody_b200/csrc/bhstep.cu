@@ -11,13 +11,15 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "bhstep.h"
 
 namespace {
 
-constexpr int kProfSteps = 64;  // steps per bh_step call that get per-stage events
-constexpr size_t kAccPad = 2048; // slack of the sorted-order acceleration buffer: equal, 32-aligned slices for up to 64 ranks
+constexpr int kProfSteps = 64;   // steps per bh_step call that get per-stage events
+constexpr size_t kAccPad = 2048; // slack of the tree-order acceleration buffer: equal, 32-aligned slices for up to 64 ranks
+constexpr int kNumTimers = BH_NUM_STAGES + 1;  // the six stages + the peer barrier
 
 thread_local std::string g_createError;
 
@@ -28,36 +30,44 @@ struct Sim {
     int vote = 16;
     int numSMs = 0;
     cudaStream_t stream = nullptr, ownStream = nullptr;
-    // device state
-    float4 *node4 = nullptr, *velacc = nullptr, *octet = nullptr, *accSorted = nullptr;
-    int *child = nullptr, *start = nullptr, *count = nullptr, *sorted = nullptr, *meta = nullptr, *oidx = nullptr, *parent = nullptr, *arrived = nullptr;
+    // device state; body arrays are double buffered (bodies are stored in tree order, see bh_kernels.cuh)
+    float4 *body4[2] = {}, *velacc[2] = {}, *cell4 = nullptr, *octet = nullptr;
+    char *accAlloc = nullptr;  // float4 acc[2][n + kAccPad] + peer flags + barrier sequence number (one IPC-exportable allocation)
+    float4 *acc = nullptr;
+    unsigned long long *flags = nullptr, *seq = nullptr;
+    int2 *ometa = nullptr;
+    int *child = nullptr, *start = nullptr, *count = nullptr, *perm = nullptr, *meta = nullptr, *parent = nullptr, *arrived = nullptr;
     float *partials = nullptr;
     bh::Scalars *sc = nullptr;
     bh::Scalars *hostSc = nullptr;  // pinned mirror
     void *staging = nullptr;
     size_t stagingBytes = 0;
+    int cur = 0;           // buffers holding the current body state
+    int treePhase = 0;     // buffers the tree (child[]) was built from
+    bool havePerm = false;   // a sort has run since the upload
+    bool permValid = false;  // perm[] refers to slots of the current buffers (false: bodies already lie in tree order)
     // launch geometry
-    int bboxGrid = 1, buildGrid = 1, summGrid = 1, sortGrid = 1;
+    int bboxGrid = 1, buildGrid = 1, summGrid = 1, sortGrid = 1, deepGrid = 1;
     // options
-    bool profiling = false, counting = false;
+    bool profiling = false, counting = false, forceDeep = false;
     int insertionOrder = 1;
-    bool haveSorted = false;
+    float4 *vertexPos = nullptr, *vertexVel = nullptr;  // fused copyVertices destinations (device pointers)
     // profiling
-    cudaEvent_t ev[kProfSteps][BH_NUM_STAGES + 1] = {};
+    cudaEvent_t ev[kProfSteps][kNumTimers + 1] = {};
     bool evCreated = false;
     int evSteps = 0;
-    double stageMs[BH_NUM_STAGES] = {};
+    double stageMs[kNumTimers] = {};
     int64_t stageLaunches[BH_NUM_STAGES] = {};
     int64_t stepsTimed = 0;
-    // peer memory (multi-GPU): every rank's accSorted mapped through CUDA IPC; two phases (ping-pong per step)
-    int nranks = 1, rank = 0, accPhase = 0;
+    // multi-GPU: the rank's slice of the tree order; peers' acceleration buffers and flags mapped through CUDA IPC
+    int sliceFirst = 0, sliceCount = 0;
+    int nranks = 1, rank = 0;
     bool p2p = false;
-    float4 *peerAcc[bh::kMaxPeers] = {};
-    // CUDA graph of one step
+    char *peerAlloc[bh::kMaxPeers] = {};
+    // CUDA graphs of one step (one per parity of the body buffers)
     bool useGraph = true;
-    cudaGraphExec_t graphExec = nullptr;
+    cudaGraphExec_t graphExec[2] = {};
     cudaStream_t graphStream = nullptr;
-    int graphInsertion = -1;
     std::string lastError;
 };
 
@@ -79,6 +89,13 @@ int fail(Sim *s, int code, const char *fmt, ...) {
     } while (0)
 
 inline Sim *S(bh_sim *p) { return reinterpret_cast<Sim *>(p); }
+inline size_t accStride(const Sim *s) { return (size_t)s->n + kAccPad; }
+inline size_t accBytes(const Sim *s) { return sizeof(float4) * 2 * accStride(s); }
+
+void dropGraphs(Sim *s) {
+    for (auto &g : s->graphExec)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
 
 int ensureStaging(Sim *s, size_t bytes) {
     if (bytes <= s->stagingBytes) return BH_OK;
@@ -101,75 +118,141 @@ int resetState(Sim *s) {
     BH_CUDA(s, cudaMemsetAsync(s->child, 0, sizeof(int) * 8 * (size_t)s->nc, s->stream));
     BH_CUDA(s, cudaMemsetAsync(s->start, 0, sizeof(int) * (size_t)s->nc, s->stream));
     BH_CUDA(s, cudaMemsetAsync(s->count, 0, sizeof(int) * (size_t)s->nc, s->stream));
-    BH_CUDA(s, cudaMemsetAsync(s->node4 + s->n, 0, sizeof(float4) * (size_t)s->nc, s->stream));
-    s->haveSorted = false;
+    BH_CUDA(s, cudaMemsetAsync(s->cell4, 0, sizeof(float4) * (size_t)s->nc, s->stream));
+    s->cur = 0;
+    s->treePhase = 0;
+    s->havePerm = false;
+    s->permValid = false;
     return BH_OK;
 }
 
-inline size_t accStride(const Sim *s) { return (size_t)s->n + kAccPad; }
-inline float4 *accPhase(const Sim *s) { return s->accSorted + (size_t)s->accPhase * accStride(s); }
-
-// force walk for sorted slots [first, first+cnt): fused velocity correction (slice = false) or
-// sorted-order acceleration output (slice = true)
-void launchForce(Sim *s, int first, int cnt, bool slice, bool counting, bool peers = false) {
+bh::PeerBuffers accDestinations(const Sim *s, bool peers) {
     bh::PeerBuffers dst;
     dst.count = 1;
-    dst.buf[0] = accPhase(s);
+    dst.buf[0] = s->acc;
+    dst.phaseStride = s->p2p ? (unsigned)accStride(s) : 0u;
     if (peers)
         for (int r = 0; r < s->nranks; ++r)
-            if (r != s->rank) dst.buf[dst.count++] = s->peerAcc[r] + (size_t)s->accPhase * accStride(s);
-#define BH_FORCE_ARGS2 s->node4, s->octet, s->oidx, s->meta, s->sorted, s->velacc, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps, s->dt
-#define BH_FORCE_DISPATCH(KERNEL, THREADS, BODIES, ARGS)                                                     \
-    do {                                                                                                     \
-        const int grid = (cnt + (BODIES) - 1) / (BODIES);                                                     \
-        if (s->vote == 16) {                                                                                 \
-            if (slice) KERNEL<16, true, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                       \
-            else if (counting) KERNEL<16, false, true><<<grid, THREADS, 0, s->stream>>>(ARGS);               \
-            else KERNEL<16, false, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                            \
-        } else {                                                                                             \
-            if (slice) KERNEL<32, true, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                       \
-            else if (counting) KERNEL<32, false, true><<<grid, THREADS, 0, s->stream>>>(ARGS);               \
-            else KERNEL<32, false, false><<<grid, THREADS, 0, s->stream>>>(ARGS);                            \
-        }                                                                                                    \
-    } while (0)
-    BH_FORCE_DISPATCH(bh::force2_kernel, bh::kForce2Threads, bh::kForce2Bodies, BH_FORCE_ARGS2);
-#undef BH_FORCE_DISPATCH
-#undef BH_FORCE_ARGS2
+            if (r != s->rank) dst.buf[dst.count++] = reinterpret_cast<float4 *>(s->peerAlloc[r]);
+    return dst;
 }
 
-int launchStage(Sim *s, int stage) {
+// force walk for tree-order slots [first, first+cnt) into the acceleration buffer(s)
+void launchWalk(Sim *s, int first, int cnt, bool peers) {
+    if (cnt <= 0) return;
+    const bh::PeerBuffers dst = accDestinations(s, peers);
+    const int *perm = s->permValid ? s->perm : nullptr;
+    const float4 *body = s->body4[s->cur];
+    const int chunks = (cnt + bh::kForce2Bodies - 1) / bh::kForce2Bodies;
+    if (s->vote == 16) {
+        const int grid = (cnt + bh::kWalkBodies - 1) / bh::kWalkBodies;
+        const int deepGrid = std::min(chunks, s->deepGrid);
+        if (s->counting) {
+            bh::walk_kernel<true><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->n, first, cnt, s->eps, s->forceDeep);
+            bh::deep_walk_kernel<16, true, true><<<deepGrid, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+        } else {
+            bh::walk_kernel<false><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->n, first, cnt, s->eps, s->forceDeep);
+            bh::deep_walk_kernel<16, true, false><<<deepGrid, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+        }
+    } else {  // 32-wide votes (not reference-exact): the shared-stack walk only
+        if (s->counting)
+            bh::deep_walk_kernel<32, false, true><<<chunks, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+        else
+            bh::deep_walk_kernel<32, false, false><<<chunks, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+    }
+}
+
+int launchBarrier(Sim *s) {
+    bh::PeerFlags pf;
+    pf.count = s->nranks;
+    pf.rank = s->rank;
+    for (int r = 0; r < s->nranks; ++r)
+        pf.flags[r] = reinterpret_cast<unsigned long long *>((r == s->rank ? s->accAlloc : s->peerAlloc[r]) + accBytes(s));
+    bh::barrier_kernel<<<1, 32, 0, s->stream>>>(pf, s->seq, s->sc, 8000000000ll);  // ~4 s at 1.9 GHz
+    BH_CUDA(s, cudaGetLastError());
+    return BH_OK;
+}
+
+// integrate (+ velocity correction when apply) (+ move every body to its tree-order slot when a fresh sort exists)
+int launchFinish(Sim *s, bool apply) {
+    const bool permute = s->insertionOrder == 1 && s->permValid;
+    const int in = s->cur, out = permute ? in ^ 1 : in;
+    const int *perm = s->permValid ? s->perm : nullptr;
+    const unsigned stride = s->p2p ? (unsigned)accStride(s) : 0u;
+    const int grid = (s->n + 255) / 256;
+#define BH_FINISH(A, P)                                                                                                       \
+    bh::finish_kernel<A, P><<<grid, 256, 0, s->stream>>>(s->body4[in], s->velacc[in], s->body4[out], s->velacc[out], s->acc, stride, \
+                                                         perm, s->sc, s->n, s->dt, s->vertexPos, s->vertexVel)
+    if (apply) { if (permute) BH_FINISH(true, true); else BH_FINISH(true, false); }
+    else { if (permute) BH_FINISH(false, true); else BH_FINISH(false, false); }
+#undef BH_FINISH
+    BH_CUDA(s, cudaGetLastError());
+    if (permute) {
+        s->cur = out;
+        s->permValid = false;  // the bodies now lie in tree order
+    }
+    return BH_OK;
+}
+
+int launchSort(Sim *s) {
+    // cooperative launch: every CTA is resident (the kernel's waits are on cells processed by resident threads)
+    const int *child = s->child, *count = s->count;
+    int *start = s->start, *perm = s->perm;
+    bh::Scalars *sc = s->sc;
+    int n = s->n, m = s->m;
+    void *args[] = {&child, &count, &start, &perm, &sc, &n, &m};
+    BH_CUDA(s, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(bh::sort_kernel), dim3(s->sortGrid), dim3(bh::kSortThreads), args, 0, s->stream));
+    s->havePerm = true;
+    s->permValid = true;
+    return BH_OK;
+}
+
+// `fused`: inside bh_step the force stage leaves the accelerations in the tree-order buffer and the integrate stage
+// applies them (one pass over the bodies); as single stages each completes its own reference semantics.
+int launchStage(Sim *s, int stage, bool fused) {
     const int n = s->n, m = s->m;
     switch (stage) {
     case BH_STAGE_BBOX:
-        bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->node4, s->child, s->start, s->count, s->arrived,
-                                                                         s->partials, s->sc, n, m);
+        bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->body4[s->cur], s->cell4, s->child, s->start, s->count,
+                                                                         s->arrived, s->partials, s->sc, n, m);
         break;
     case BH_STAGE_BUILD:
-        bh::build_kernel<<<s->buildGrid, bh::kBuildThreads, 0, s->stream>>>(
-            s->node4, s->child, s->start, s->count, s->parent, s->arrived,
-            (s->insertionOrder == 1 && s->haveSorted) ? s->sorted : nullptr, s->sc, n, m);
+        bh::build_kernel<<<s->buildGrid, bh::kBuildThreads, 0, s->stream>>>(s->body4[s->cur], s->cell4, s->child, s->start, s->count,
+                                                                            s->parent, s->arrived, s->sc, n, m);
+        s->treePhase = s->cur;
         break;
     case BH_STAGE_SUMMARIZE:
-        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->node4, s->child, s->octet, s->oidx, s->meta, s->count,
-                                                                              s->parent, s->arrived, s->sc, n, m);
+        bh::summarize_kernel<<<s->summGrid, bh::kSummThreads, 0, s->stream>>>(s->body4[s->cur], s->cell4, s->child, s->octet, s->ometa,
+                                                                              s->meta, s->count, s->parent, s->arrived, s->sc, n, m,
+                                                                              s->thetaMacro, s->eps);
         break;
-    case BH_STAGE_SORT:
-        bh::sort_kernel<<<s->sortGrid, bh::kSortThreads, 0, s->stream>>>(s->child, s->count, s->start, s->sorted, s->sc, n, m);
-        s->haveSorted = true;
-        break;
-    case BH_STAGE_FORCE: {
-        if (s->counting) BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
-        launchForce(s, 0, n, false, s->counting);
+    case BH_STAGE_SORT: {
+        int rc = launchSort(s);
+        if (rc) return rc;
         break;
     }
-    case BH_STAGE_INTEGRATE:
-        bh::integrate_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, s->sc, n, s->dt);
+    case BH_STAGE_FORCE: {
+        if (s->counting) BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
+        const bool sliced = fused && s->p2p;
+        launchWalk(s, sliced ? s->sliceFirst : 0, sliced ? s->sliceCount : n, sliced);
+        if (!fused) {
+            const unsigned stride = s->p2p ? (unsigned)accStride(s) : 0u;
+            bh::apply_acc_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->acc, stride, s->permValid ? s->perm : nullptr,
+                                                                       s->velacc[s->cur], s->sc, n, s->dt);
+        }
         break;
+    }
+    case BH_STAGE_INTEGRATE: {
+        int rc = launchFinish(s, fused);
+        if (rc) return rc;
+        break;
+    }
     default:
         return fail(s, BH_ERR_ARG, "unknown stage %d", stage);
     }
     BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[stage]++;
+    s->stageLaunches[stage] += (stage == BH_STAGE_FORCE && s->vote == 16) ? 2 : 1;
+    if (stage == BH_STAGE_FORCE && !fused) s->stageLaunches[stage]++;
     return BH_OK;
 }
 
@@ -179,7 +262,7 @@ int finish(Sim *s) {
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     if (s->profiling && s->evSteps > 0) {
         for (int i = 0; i < s->evSteps; ++i)
-            for (int st = 0; st < BH_NUM_STAGES; ++st) {
+            for (int st = 0; st < kNumTimers; ++st) {
                 float ms = 0.0f;
                 if (cudaEventElapsedTime(&ms, s->ev[i][st], s->ev[i][st + 1]) == cudaSuccess) s->stageMs[st] += ms;
             }
@@ -187,48 +270,91 @@ int finish(Sim *s) {
         s->evSteps = 0;
     }
     if (s->hostSc->error != 0) {
-        fail(s, s->hostSc->error, "device error buffer = %d (%s)", s->hostSc->error,
-             s->hostSc->error == 1 ? "cell pool exhausted or tree deeper than 64 levels" : "device-side wait exceeded its spin budget");
-        return s->hostSc->error;
+        const int e = s->hostSc->error;
+        fail(s, e, "device error buffer = %d (%s)", e,
+             e == 1 ? "cell pool exhausted or tree deeper than 64 levels"
+                    : e == 2 ? "device-side wait exceeded its spin budget" : "peer barrier timed out");
+        return e;
     }
     return BH_OK;
 }
 
-// One step = six launches with fixed arguments once a sorted order exists: captured once into a CUDA graph and
-// replayed (one launch call per step instead of six; matters for small universes such as the reference's 32 768-body
-// default, where a step is a few hundred microseconds).  Not used while per-stage events or counters are on.
+// The launches of one step in order; timers[] (optional) = kNumTimers + 1 events recorded between them in the order
+// bbox, build, summarise, sort, force, barrier, finish.
+int launchStep(Sim *s, cudaEvent_t *timers) {
+    static const int order[kNumTimers] = {BH_STAGE_BBOX, BH_STAGE_BUILD, BH_STAGE_SUMMARIZE, BH_STAGE_SORT, BH_STAGE_FORCE, -1,
+                                          BH_STAGE_INTEGRATE};
+    // timer slots: stage index for the six stages, kTimerBarrier for the barrier; events are recorded in launch order
+    for (int k = 0; k < kNumTimers; ++k) {
+        if (timers) BH_CUDA(s, cudaEventRecord(timers[k], s->stream));
+        if (order[k] < 0) {
+            if (s->p2p) {
+                int rc = launchBarrier(s);
+                if (rc) return rc;
+                s->stageLaunches[BH_STAGE_FORCE]++;
+            }
+            continue;
+        }
+        int rc = launchStage(s, order[k], true);
+        if (rc) return rc;
+    }
+    if (timers) BH_CUDA(s, cudaEventRecord(timers[kNumTimers], s->stream));
+    return BH_OK;
+}
+
+// One step = a fixed sequence of launches with fixed arguments per parity of the body buffers: captured once into a
+// CUDA graph per parity and replayed (one launch call per step; matters for small universes such as the reference's
+// 32 768-body default, where a step is a few hundred microseconds, and for the multi-GPU step, whose cross-rank
+// barrier is a kernel of its own).  Not used while per-stage events or counters are on.
 int graphStep(Sim *s) {
-    if (!s->graphExec || s->graphStream != s->stream || s->graphInsertion != s->insertionOrder) {
-        if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+    if (s->graphStream != s->stream) { dropGraphs(s); s->graphStream = s->stream; }
+    const int parity = s->cur;
+    const bool willPermute = s->insertionOrder == 1;
+    if (!s->graphExec[parity]) {
         cudaGraph_t graph = nullptr;
+        const int cur0 = s->cur, tree0 = s->treePhase;
+        const bool have0 = s->havePerm, valid0 = s->permValid;
+        int64_t launches0[BH_NUM_STAGES];
+        memcpy(launches0, s->stageLaunches, sizeof launches0);
         if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();    // e.g. a stream that cannot be captured: plain launches from now on
             s->useGraph = false;
             return BH_ERR_ARG;     // tells stepAsync to launch this step the ordinary way
         }
-        int rc = BH_OK;
-        for (int st = 0; st < BH_NUM_STAGES && rc == BH_OK; ++st) rc = launchStage(s, st);
+        const int rc = launchStep(s, nullptr);
         const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-        if (rc != BH_OK || e != cudaSuccess) {
+        // the capture did not run anything: restore the host-side state
+        s->cur = cur0; s->treePhase = tree0; s->havePerm = have0; s->permValid = valid0;
+        memcpy(s->stageLaunches, launches0, sizeof launches0);
+        if (rc != BH_OK || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
-            return rc != BH_OK ? rc : fail(s, BH_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            s->useGraph = false;   // e.g. a driver that cannot capture a cooperative launch: plain launches from now on
+            return BH_ERR_ARG;
         }
-        for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st]--;  // the capture did not run anything
-        const cudaError_t ei = cudaGraphInstantiate(&s->graphExec, graph, 0);
+        const cudaError_t ei = cudaGraphInstantiate(&s->graphExec[parity], graph, 0);
         cudaGraphDestroy(graph);
-        if (ei != cudaSuccess) { s->graphExec = nullptr; return fail(s, BH_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
-        s->graphStream = s->stream;
-        s->graphInsertion = s->insertionOrder;
+        if (ei != cudaSuccess) {
+            s->graphExec[parity] = nullptr;
+            cudaGetLastError();
+            s->useGraph = false;
+            return BH_ERR_ARG;
+        }
     }
-    BH_CUDA(s, cudaGraphLaunch(s->graphExec, s->stream));
-    for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st]++;
+    BH_CUDA(s, cudaGraphLaunch(s->graphExec[parity], s->stream));
+    // host-side mirror of what the replayed launches did
+    s->treePhase = parity;
+    s->havePerm = true;
+    if (willPermute) { s->cur = parity ^ 1; s->permValid = false; } else { s->permValid = true; }
+    for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st] += (st == BH_STAGE_FORCE && s->vote == 16) ? 2 : 1;
+    if (s->p2p) s->stageLaunches[BH_STAGE_FORCE]++;  // the peer barrier
     return BH_OK;
 }
 
 int stepAsync(Sim *s, int nsteps) {
     for (int i = 0; i < nsteps; ++i) {
         // (the legacy default stream cannot be captured)
-        if (s->useGraph && !s->profiling && !s->counting && s->haveSorted && s->stream != nullptr) {
+        if (s->useGraph && !s->profiling && !s->counting && s->stream != nullptr) {
             int rc = graphStep(s);
             if (rc == BH_OK) continue;
             if (s->useGraph) return rc;  // a real failure; otherwise capture was refused and the graph is now off
@@ -239,47 +365,45 @@ int stepAsync(Sim *s, int nsteps) {
                 for (auto &e : row) BH_CUDA(s, cudaEventCreate(&e));
             s->evCreated = true;
         }
-        for (int st = 0; st < BH_NUM_STAGES; ++st) {
-            if (prof) BH_CUDA(s, cudaEventRecord(s->ev[s->evSteps][st], s->stream));
-            int rc = launchStage(s, st);
-            if (rc) return rc;
-        }
-        if (prof) {
-            BH_CUDA(s, cudaEventRecord(s->ev[s->evSteps][BH_NUM_STAGES], s->stream));
-            s->evSteps++;
-        }
+        int rc = launchStep(s, prof ? s->ev[s->evSteps] : nullptr);
+        if (rc) return rc;
+        if (prof) s->evSteps++;
     }
     return BH_OK;
 }
 
 int singleStage(Sim *s, int stage) {
-    const bool prof = s->profiling && s->evSteps < kProfSteps;
-    if (prof) {
+    if (s->profiling) {
         // single stages are timed through one-off events folded into the same accumulators
         cudaEvent_t a, b;
         BH_CUDA(s, cudaEventCreate(&a));
         BH_CUDA(s, cudaEventCreate(&b));
         BH_CUDA(s, cudaEventRecord(a, s->stream));
-        int rc = launchStage(s, stage);
+        int rc = launchStage(s, stage, false);
         if (rc) return rc;
         BH_CUDA(s, cudaEventRecord(b, s->stream));
         rc = finish(s);
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) s->stageMs[stage] += ms;
+        // timer slots follow the launch order of a step: 0-4 = bbox..force, 5 = peer barrier, 6 = finish
+        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) s->stageMs[stage == BH_STAGE_INTEGRATE ? kNumTimers - 1 : stage] += ms;
         cudaEventDestroy(a);
         cudaEventDestroy(b);
         return rc;
     }
-    int rc = launchStage(s, stage);
+    int rc = launchStage(s, stage, false);
     if (rc) return rc;
     return finish(s);
+}
+
+bool validSlice(const Sim *s, int32_t first, int32_t count) {
+    return first >= 0 && count >= 0 && (int64_t)first + count <= s->n && (first % s->vote) == 0;
 }
 
 }  // namespace
 
 extern "C" {
 
-int32_t bh_abi_version(void) { return 1; }
+int32_t bh_abi_version(void) { return 2; }
 
 int32_t bh_number_of_nodes(int32_t nbodies) {
     // GPUBH:219-227 with maxComputeUnits = 16 (GPUBH:126) and WARPSIZE = 16 (GPUBH:47)
@@ -297,8 +421,8 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     if (nbodies < 1) return fail(nullptr, BH_ERR_ARG, "nbodies must be >= 1");
     if (vote_width != 16 && vote_width != 32) return fail(nullptr, BH_ERR_ARG, "vote_width must be 16 or 32");
     const int32_t m = bh_number_of_nodes(nbodies);
-    // child rows are addressed as 8*(cell-N) in size_t; node indices must fit int32
-    if (m < 0) return fail(nullptr, BH_ERR_ARG, "nbodies too large for 32-bit node indices");
+    // child rows are addressed as 8*(cell-N) in size_t; node indices must fit int32, walk entries 27 bits
+    if (m < 0 || (int64_t)m - nbodies + 1 > (int64_t)bh::kEntryMask) return fail(nullptr, BH_ERR_ARG, "nbodies too large (at most 2^27 - 2 cells)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, BH_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
@@ -314,6 +438,8 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     s->eps = eps2;
     s->dt = dt;
     s->vote = vote_width;
+    s->sliceFirst = 0;
+    s->sliceCount = nbodies;
     auto bail = [&](int code, const char *what, cudaError_t e) {
         fail(nullptr, code, "%s: %s", what, cudaGetErrorString(e));
         bh_destroy(reinterpret_cast<bh_sim *>(s));
@@ -324,28 +450,35 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaGetDeviceProperties", e);
     s->numSMs = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) return bail(BH_ERR_CUDA, "device cannot launch cooperative kernels", cudaErrorNotSupported);
     if ((e = cudaStreamCreateWithFlags(&s->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaStreamCreate", e);
     s->stream = s->ownStream;
     const size_t n = nbodies, nc = s->nc;
 #define BH_ALLOC(ptr, bytes) \
     if ((e = cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes))) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMalloc " #ptr, e)
-    BH_ALLOC(s->node4, sizeof(float4) * ((size_t)m + 1));
-    BH_ALLOC(s->velacc, sizeof(float4) * 2 * n);
+    for (int b = 0; b < 2; ++b) {
+        BH_ALLOC(s->body4[b], sizeof(float4) * n);
+        BH_ALLOC(s->velacc[b], sizeof(float4) * 2 * n);
+    }
+    BH_ALLOC(s->cell4, sizeof(float4) * nc);
     BH_ALLOC(s->octet, sizeof(float4) * 8 * nc);
-    BH_ALLOC(s->accSorted, sizeof(float4) * 2 * (n + kAccPad));  // two phases, see bh_ipc_set_peers
+    BH_ALLOC(s->ometa, sizeof(int2) * 8 * nc);
+    BH_ALLOC(s->accAlloc, accBytes(s) + 512);  // two phases, peer flags, barrier sequence number
     BH_ALLOC(s->child, sizeof(int) * 8 * nc);
     BH_ALLOC(s->start, sizeof(int) * nc);
     BH_ALLOC(s->count, sizeof(int) * nc);
     BH_ALLOC(s->meta, sizeof(int) * nc);
-    BH_ALLOC(s->oidx, sizeof(int) * 8 * nc);
     BH_ALLOC(s->parent, sizeof(int) * nc);
     BH_ALLOC(s->arrived, sizeof(int) * nc);
-    BH_ALLOC(s->sorted, sizeof(int) * n);
+    BH_ALLOC(s->perm, sizeof(int) * n);
     BH_ALLOC(s->sc, sizeof(bh::Scalars));
 #undef BH_ALLOC
+    s->acc = reinterpret_cast<float4 *>(s->accAlloc);
+    s->flags = reinterpret_cast<unsigned long long *>(s->accAlloc + accBytes(s));
+    s->seq = s->flags + bh::kMaxPeers;
     if ((e = cudaMallocHost(reinterpret_cast<void **>(&s->hostSc), sizeof(bh::Scalars))) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMallocHost", e);
-    // launch geometry: streaming kernels a few CTAs per SM; the two kernels that wait on
-    // other threads (summarise, sort) exactly as many CTAs as are resident at once.
+    // launch geometry: streaming kernels a few CTAs per SM; sort (which waits on other threads) exactly as many
+    // CTAs as are resident at once (and it is launched cooperatively).
     int perSM = 1;
     s->bboxGrid = (int)std::min<size_t>((n + bh::kBboxThreads - 1) / bh::kBboxThreads, (size_t)s->numSMs * 4);
     if ((e = cudaMalloc(reinterpret_cast<void **>(&s->partials), sizeof(float) * 6 * s->bboxGrid)) != cudaSuccess) return bail(BH_ERR_ALLOC, "cudaMalloc partials", e);
@@ -357,10 +490,13 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     // tiny problems: do not launch more waiting threads than there can be cells
     const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
     s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
-    if ((e = cudaMemsetAsync(s->node4, 0, sizeof(float4) * ((size_t)m + 1), s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
-    cudaMemsetAsync(s->velacc, 0, sizeof(float4) * 2 * n, s->stream);
-    cudaMemsetAsync(s->sorted, 0, sizeof(int) * n, s->stream);
-    cudaMemsetAsync(s->accSorted, 0, sizeof(float4) * 2 * (n + kAccPad), s->stream);
+    s->deepGrid = s->numSMs * 8;
+    for (int b = 0; b < 2; ++b) {
+        if ((e = cudaMemsetAsync(s->body4[b], 0, sizeof(float4) * n, s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
+        cudaMemsetAsync(s->velacc[b], 0, sizeof(float4) * 2 * n, s->stream);
+    }
+    cudaMemsetAsync(s->perm, 0, sizeof(int) * n, s->stream);
+    cudaMemsetAsync(s->accAlloc, 0, accBytes(s) + 512, s->stream);
     if (resetState(s) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
         g_createError = s->lastError.empty() ? "initial reset failed" : s->lastError;
         bh_destroy(reinterpret_cast<bh_sim *>(s));
@@ -370,16 +506,26 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     return BH_OK;
 }
 
+static void closePeers(Sim *s) {
+    for (int r = 0; r < bh::kMaxPeers; ++r) {
+        if (s->peerAlloc[r] && s->peerAlloc[r] != s->accAlloc) cudaIpcCloseMemHandle(s->peerAlloc[r]);
+        s->peerAlloc[r] = nullptr;
+    }
+    s->p2p = false;
+    s->nranks = 1;
+    s->rank = 0;
+}
+
 void bh_destroy(bh_sim *sim) {
     if (!sim) return;
     Sim *s = S(sim);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
-    for (int r = 0; r < s->nranks; ++r)
-        if (s->p2p && r != s->rank && s->peerAcc[r]) cudaIpcCloseMemHandle(s->peerAcc[r]);
-    cudaFree(s->node4); cudaFree(s->velacc); cudaFree(s->octet); cudaFree(s->accSorted);
-    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->sorted); cudaFree(s->meta); cudaFree(s->oidx); cudaFree(s->parent); cudaFree(s->arrived);
+    dropGraphs(s);
+    closePeers(s);
+    for (int b = 0; b < 2; ++b) { cudaFree(s->body4[b]); cudaFree(s->velacc[b]); }
+    cudaFree(s->cell4); cudaFree(s->octet); cudaFree(s->ometa); cudaFree(s->accAlloc);
+    cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->perm); cudaFree(s->meta); cudaFree(s->parent); cudaFree(s->arrived);
     cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
@@ -396,7 +542,7 @@ void bh_destroy(bh_sim *sim) {
 
 int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
     BH_ENTER(sim);
-    if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }  // kernel arguments change
+    dropGraphs(s);  // kernel arguments change
     s->thetaMacro = theta_macro;
     return BH_OK;
 }
@@ -436,7 +582,23 @@ int bh_set_graph(bh_sim *sim, int32_t on) {
 int bh_set_insertion_order(bh_sim *sim, int32_t mode) {
     BH_ENTER(sim);
     if (mode != 0 && mode != 1) return fail(s, BH_ERR_ARG, "insertion order must be 0 or 1");
+    if (mode != s->insertionOrder) dropGraphs(s);
     s->insertionOrder = mode;
+    return BH_OK;
+}
+
+int bh_set_force_deep_walk(bh_sim *sim, int32_t on) {
+    BH_ENTER(sim);
+    if ((on != 0) != s->forceDeep) dropGraphs(s);
+    s->forceDeep = on != 0;
+    return BH_OK;
+}
+
+int bh_set_vertex_buffers(bh_sim *sim, void *pos4_device, void *vel4_device) {
+    BH_ENTER(sim);
+    dropGraphs(s);
+    s->vertexPos = static_cast<float4 *>(pos4_device);
+    s->vertexVel = static_cast<float4 *>(vel4_device);
     return BH_OK;
 }
 
@@ -458,8 +620,8 @@ static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind) {
     }
     int rc = resetState(s);
     if (rc) return rc;
-    bh::pack_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], s->node4,
-                                                              s->velacc, s->sorted, s->n);
+    bh::pack_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], s->body4[0],
+                                                              s->velacc[0], s->perm, s->n);
     BH_CUDA(s, cudaGetLastError());
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     return BH_OK;
@@ -486,7 +648,7 @@ int bh_sort(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_SORT); 
 int bh_calculate_force(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_FORCE); }
 int bh_integrate(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_INTEGRATE); }
 
-int bh_stage_async(bh_sim *sim, int32_t stage) { BH_ENTER(sim); return launchStage(s, stage); }
+int bh_stage_async(bh_sim *sim, int32_t stage) { BH_ENTER(sim); return launchStage(s, stage, false); }
 
 int bh_step_async(bh_sim *sim, int32_t nsteps) {
     BH_ENTER(sim);
@@ -515,33 +677,78 @@ int bh_step(bh_sim *sim, int32_t nsteps) {
 
 int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
     BH_ENTER(sim);
-    if (first < 0 || count < 0 || (int64_t)first + count > s->n || (first % s->vote) != 0)
-        return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
+    if (!validSlice(s, first, count)) return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
     if (count == 0) return BH_OK;
-    launchForce(s, first, count, true, false);
+    launchWalk(s, first, count, false);
     BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[BH_STAGE_FORCE]++;
+    s->stageLaunches[BH_STAGE_FORCE] += s->vote == 16 ? 2 : 1;
     return BH_OK;
+}
+
+int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count) {
+    BH_ENTER(sim);
+    if (!s->p2p) return fail(s, BH_ERR_ARG, "bh_ipc_set_peers has not been called");
+    if (!validSlice(s, first, count)) return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
+    if (count == 0) return BH_OK;
+    launchWalk(s, first, count, true);
+    BH_CUDA(s, cudaGetLastError());
+    s->stageLaunches[BH_STAGE_FORCE] += s->vote == 16 ? 2 : 1;
+    return BH_OK;
+}
+
+int bh_peer_barrier(bh_sim *sim) {
+    BH_ENTER(sim);
+    if (!s->p2p) return fail(s, BH_ERR_ARG, "bh_ipc_set_peers has not been called");
+    return launchBarrier(s);
 }
 
 int bh_apply_acceleration(bh_sim *sim) {
     BH_ENTER(sim);
-    bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(accPhase(s), s->sorted, s->velacc, s->sc, s->n, s->dt);
+    const unsigned stride = s->p2p ? (unsigned)accStride(s) : 0u;
+    bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->acc, stride, s->permValid ? s->perm : nullptr, s->velacc[s->cur],
+                                                                   s->sc, s->n, s->dt);
     BH_CUDA(s, cudaGetLastError());
     s->stageLaunches[BH_STAGE_FORCE]++;
-    if (s->p2p) s->accPhase ^= 1;  // peers may already store the next step's slices while this kernel still reads
     return BH_OK;
 }
 
-void *bh_acc_sorted_device_ptr(bh_sim *sim) { return sim ? S(sim)->accSorted : nullptr; }
+int bh_finish_async(bh_sim *sim) {
+    BH_ENTER(sim);
+    int rc = launchFinish(s, true);
+    if (rc == BH_OK) s->stageLaunches[BH_STAGE_INTEGRATE]++;
+    return rc;
+}
+
+void *bh_acc_sorted_device_ptr(bh_sim *sim) { return sim ? S(sim)->acc : nullptr; }
+
+int bh_set_slice(bh_sim *sim, int32_t first, int32_t count) {
+    BH_ENTER(sim);
+    if (!validSlice(s, first, count)) return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
+    if (!s->p2p && (first != 0 || count != s->n))
+        return fail(s, BH_ERR_ARG, "a slice smaller than the universe needs peer memory (bh_ipc_set_peers): the step's all-gather runs over it");
+    dropGraphs(s);
+    s->sliceFirst = first;
+    s->sliceCount = count;
+    return BH_OK;
+}
 
 int bh_ipc_export(bh_sim *sim, void *handle64) {
     BH_ENTER(sim);
     if (!handle64) return fail(s, BH_ERR_ARG, "handle64 is NULL");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     cudaIpcMemHandle_t h;
-    BH_CUDA(s, cudaIpcGetMemHandle(&h, s->accSorted));
+    BH_CUDA(s, cudaIpcGetMemHandle(&h, s->accAlloc));
     memcpy(handle64, &h, sizeof h);
+    return BH_OK;
+}
+
+int bh_ipc_clear_peers(bh_sim *sim) {
+    BH_ENTER(sim);
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    dropGraphs(s);
+    closePeers(s);
+    s->sliceFirst = 0;
+    s->sliceCount = s->n;
     return BH_OK;
 }
 
@@ -549,30 +756,25 @@ int bh_ipc_set_peers(bh_sim *sim, int32_t nranks, int32_t my_rank, const void *h
     BH_ENTER(sim);
     if (nranks < 1 || nranks > bh::kMaxPeers || my_rank < 0 || my_rank >= nranks || !handles)
         return fail(s, BH_ERR_ARG, "bad peer set (at most %d ranks)", bh::kMaxPeers);
+    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    dropGraphs(s);
+    closePeers(s);
     for (int r = 0; r < nranks; ++r) {
-        if (r == my_rank) { s->peerAcc[r] = s->accSorted; continue; }
+        if (r == my_rank) { s->peerAlloc[r] = s->accAlloc; continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, static_cast<const char *>(handles) + 64 * (size_t)r, sizeof h);
         void *p = nullptr;
-        BH_CUDA(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        s->peerAcc[r] = static_cast<float4 *>(p);
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            closePeers(s);  // release what was opened: the caller falls back to its own all-gather
+            return fail(s, BH_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        s->peerAlloc[r] = static_cast<char *>(p);
     }
     s->nranks = nranks;
     s->rank = my_rank;
     s->p2p = nranks > 1;
-    s->accPhase = 0;
-    return BH_OK;
-}
-
-int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count) {
-    BH_ENTER(sim);
-    if (!s->p2p) return fail(s, BH_ERR_ARG, "bh_ipc_set_peers has not been called");
-    if (first < 0 || count < 0 || (int64_t)first + count > s->n || (first % s->vote) != 0)
-        return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
-    if (count == 0) return BH_OK;
-    launchForce(s, first, count, true, false, true);
-    BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[BH_STAGE_FORCE]++;
     return BH_OK;
 }
 
@@ -610,40 +812,51 @@ int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
     int rc = ensureStaging(s, 4 * (size_t)count);
     if (rc) return rc;
     const unsigned grid = (unsigned)((count + 255) / 256);
+    const unsigned gridBodies = (unsigned)((std::max<int64_t>(count, s->n) + 255) / 256);  // bodies scatter to the host's numbering
+    float *fout = static_cast<float *>(s->staging);
+    int *iout = static_cast<int *>(s->staging);
+    const float4 *body = s->body4[s->cur], *va = s->velacc[s->cur];
     switch (which) {
     case BH_POS_X: case BH_POS_Y: case BH_POS_Z:
-        bh::export_node_kernel<<<grid, 256, 0, s->stream>>>(s->node4, which - BH_POS_X, static_cast<float *>(s->staging), count);
-        break;
-    case BH_MASS:
-        bh::export_node_kernel<<<grid, 256, 0, s->stream>>>(s->node4, 3, static_cast<float *>(s->staging), count);
+        bh::export_float_kernel<<<gridBodies, 256, 0, s->stream>>>(body, va, s->cell4, which - BH_POS_X, fout, s->n, count);
         break;
     case BH_VEL_X: case BH_VEL_Y: case BH_VEL_Z:
-        bh::export_velacc_kernel<<<grid, 256, 0, s->stream>>>(s->velacc, 0, which - BH_VEL_X, static_cast<float *>(s->staging), s->n, count);
+        bh::export_float_kernel<<<gridBodies, 256, 0, s->stream>>>(body, va, s->cell4, 3 + which - BH_VEL_X, fout, s->n, count);
         break;
     case BH_ACC_X: case BH_ACC_Y: case BH_ACC_Z:
-        bh::export_velacc_kernel<<<grid, 256, 0, s->stream>>>(s->velacc, 1, which - BH_ACC_X, static_cast<float *>(s->staging), s->n, count);
+        bh::export_float_kernel<<<gridBodies, 256, 0, s->stream>>>(body, va, s->cell4, 6 + which - BH_ACC_X, fout, s->n, count);
+        break;
+    case BH_MASS:
+        bh::export_float_kernel<<<gridBodies, 256, 0, s->stream>>>(body, va, s->cell4, 9, fout, s->n, count);
         break;
     case BH_BODY_COUNT:
-        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->count, s->n, static_cast<int *>(s->staging), count);
+        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->count, s->n, bh::kCountMask, iout, count);
         break;
     case BH_START:
-        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->start, s->n, static_cast<int *>(s->staging), count);
+        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->start, s->n, -1, iout, count);
         break;
     case BH_CHILD:
-        bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->child, 8 * (long long)s->n, static_cast<int *>(s->staging), count);
+        bh::export_child_kernel<<<grid, 256, 0, s->stream>>>(s->child, s->velacc[s->treePhase], s->n, iout, count);
         break;
-    case BH_SORTED: {
-        const int64_t head = std::min<int64_t>(count, s->n);
-        BH_CUDA(s, cudaMemcpyAsync(s->staging, s->sorted, 4 * (size_t)head, cudaMemcpyDeviceToDevice, s->stream));
-        if (count > head) BH_CUDA(s, cudaMemsetAsync(static_cast<int *>(s->staging) + head, 0, 4 * (size_t)(count - head), s->stream));
+    case BH_SORTED:
+        if (!s->havePerm) BH_CUDA(s, cudaMemsetAsync(iout, 0, 4 * (size_t)count, s->stream));  // GPUBH:178: zeros until the first sort
+        else bh::export_sorted_kernel<<<grid, 256, 0, s->stream>>>(s->perm, va, s->permValid ? 1 : 0, s->n, iout, count);
         break;
-    }
     default:
         return fail(s, BH_ERR_ARG, "unknown buffer %d", which);
     }
     BH_CUDA(s, cudaGetLastError());
     BH_CUDA(s, cudaMemcpyAsync(dst, s->staging, 4 * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    return BH_OK;
+}
+
+int bh_copy_vertices_device(bh_sim *sim, void *pos4_device, void *vel4_device) {
+    BH_ENTER(sim);
+    if (!pos4_device && !vel4_device) return BH_OK;
+    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], static_cast<float4 *>(pos4_device),
+                                                                       static_cast<float4 *>(vel4_device), s->n);
+    BH_CUDA(s, cudaGetLastError());
     return BH_OK;
 }
 
@@ -654,10 +867,15 @@ int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4) {
     int rc = ensureStaging(s, 2 * bytes);
     if (rc) return rc;
     float4 *dp = static_cast<float4 *>(s->staging), *dv = dp + s->n;
-    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, pos4 ? dp : nullptr, vel4 ? dv : nullptr, s->n);
+    // the position half travels while the velocity half is still being written
+    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], pos4 ? dp : nullptr, nullptr, s->n);
     BH_CUDA(s, cudaGetLastError());
     if (pos4) BH_CUDA(s, cudaMemcpyAsync(pos4, dp, bytes, cudaMemcpyDeviceToHost, s->stream));
-    if (vel4) BH_CUDA(s, cudaMemcpyAsync(vel4, dv, bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (vel4) {
+        bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], nullptr, dv, s->n);
+        BH_CUDA(s, cudaGetLastError());
+        BH_CUDA(s, cudaMemcpyAsync(vel4, dv, bytes, cudaMemcpyDeviceToHost, s->stream));
+    }
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     return BH_OK;
 }
@@ -675,21 +893,22 @@ int bh_stats(bh_sim *sim, bh_stats_t *out) {
     out->step = s->hostSc->step;
     out->error = s->hostSc->error;
     out->steps_timed = s->stepsTimed;
+    // events are recorded in launch order: slots 0-4 = bbox..force, 5 = barrier, 6 = finish
     for (int i = 0; i < BH_NUM_STAGES; ++i) {
-        out->stage_ms[i] = s->stageMs[i];
+        out->stage_ms[i] = s->stageMs[i == BH_STAGE_INTEGRATE ? kNumTimers - 1 : i];
         out->stage_launches[i] = s->stageLaunches[i];
     }
+    out->barrier_ms = s->stageMs[BH_STAGE_INTEGRATE];
     out->interactions = (int64_t)s->hostSc->interactions;
     out->opens = (int64_t)s->hostSc->opens;
+    out->deep_walk = s->hostSc->deep;
     return BH_OK;
 }
 
 int bh_reset_stats(bh_sim *sim) {
     BH_ENTER(sim);
-    for (int i = 0; i < BH_NUM_STAGES; ++i) {
-        s->stageMs[i] = 0.0;
-        s->stageLaunches[i] = 0;
-    }
+    for (auto &v : s->stageMs) v = 0.0;
+    for (auto &v : s->stageLaunches) v = 0;
     s->stepsTimed = 0;
     return BH_OK;
 }
@@ -701,7 +920,7 @@ int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, flo
     if (kind < 0 || kind > 2) return fail(s, BH_ERR_ARG, "unknown universe kind %d", kind);
     int rc = resetState(s);
     if (rc) return rc;
-    bh::generate_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->node4, s->velacc, s->sorted, s->n, kind, seed, p0, p1, p2);
+    bh::generate_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[0], s->velacc[0], s->perm, s->n, kind, seed, p0, p1, p2);
     BH_CUDA(s, cudaGetLastError());
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     return BH_OK;
@@ -714,9 +933,9 @@ int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
     if (rc) return rc;
     double *d = static_cast<double *>(s->staging);
     BH_CUDA(s, cudaMemsetAsync(d, 0, 8 * sizeof(double), s->stream));
-    bh::kinetic_kernel<<<std::min((s->n + 255) / 256, s->numSMs * 8), 256, 0, s->stream>>>(s->node4, s->velacc, d, s->n);
+    bh::kinetic_kernel<<<std::min((s->n + 255) / 256, s->numSMs * 8), 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], d, s->n);
     if (with_potential)
-        bh::potential_kernel<<<(s->n + bh::kPotTile - 1) / bh::kPotTile, bh::kPotTile, 0, s->stream>>>(s->node4, d, s->n, s->eps);
+        bh::potential_kernel<<<(s->n + bh::kPotTile - 1) / bh::kPotTile, bh::kPotTile, 0, s->stream>>>(s->body4[s->cur], d, s->n, s->eps);
     BH_CUDA(s, cudaGetLastError());
     double h[8];
     BH_CUDA(s, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));
@@ -728,50 +947,71 @@ int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
 
 // ---- .universe files (Java ObjectOutputStream layout, UniverseSerializer.java:25-34) ----
 namespace {
+const unsigned char kMagic[6] = {0xAC, 0xED, 0x00, 0x05, 0x77, 0x04};  // stream header + TC_BLOCKDATA(4) = writeInt
+const unsigned char kClassDesc[] = {0x72, 0x00, 0x02, '[', 'F', 0x0B, 0x9C, 0x81, 0x89, 0x22, 0xE0, 0x0C, 0x42, 0x02, 0x00, 0x00, 0x78, 0x70};
+const unsigned char kClassRef[] = {0x71, 0x00, 0x7E, 0x00, 0x00};
+
 struct UniverseFile {
     int32_t n = 0;
     std::string error;
-    float *arrays[7] = {};
-    ~UniverseFile() { for (auto *a : arrays) free(a); }
+    std::vector<float> arrays[7];
 };
 uint32_t be32(const unsigned char *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
-bool readUniverse(const char *path, bool headerOnly, UniverseFile &u) {
-    FILE *f = fopen(path, "rb");
-    if (!f) { u.error = std::string("cannot open ") + path; return false; }
+void putBe32(unsigned char *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+
+// expect > 0: the body count the caller needs (checked before anything is allocated); 0 = any
+bool readUniverseBody(FILE *f, bool headerOnly, int32_t expect, UniverseFile &u) {
     unsigned char hdr[10];
-    static const unsigned char magic[6] = {0xAC, 0xED, 0x00, 0x05, 0x77, 0x04};  // stream header + TC_BLOCKDATA(4) = writeInt
-    if (fread(hdr, 1, 10, f) != 10 || memcmp(hdr, magic, 6) != 0) { fclose(f); u.error = "not a .universe file (Java stream with a leading writeInt expected)"; return false; }
+    if (fread(hdr, 1, 10, f) != 10 || memcmp(hdr, kMagic, 6) != 0) { u.error = "not a .universe file (Java stream with a leading writeInt expected)"; return false; }
     u.n = (int32_t)be32(hdr + 6);
-    if (headerOnly) { fclose(f); return true; }
-    static const unsigned char classDesc[] = {0x72, 0x00, 0x02, '[', 'F', 0x0B, 0x9C, 0x81, 0x89, 0x22, 0xE0, 0x0C, 0x42, 0x02, 0x00, 0x00, 0x78, 0x70};
-    static const unsigned char classRef[] = {0x71, 0x00, 0x7E, 0x00, 0x00};
+    if (u.n <= 0) { u.error = "invalid body count in the file header"; return false; }
+    if (headerOnly) return true;
+    if (expect > 0 && u.n != expect) {  // SerializedUniverseGenerator.java:41-42 IllegalStateException
+        char msg[160];
+        snprintf(msg, sizeof msg, "invalid amount of bodies for serialized universe (%d in the file, %d in the simulation)", u.n, expect);
+        u.error = msg;
+        return false;
+    }
+    std::vector<unsigned char> buf(4 * (size_t)u.n);
     for (int a = 0; a < 7; ++a) {
         unsigned char tag[32];
-        if (fread(tag, 1, 2, f) != 2 || tag[0] != 0x75) { fclose(f); u.error = "expected TC_ARRAY"; return false; }
+        if (fread(tag, 1, 2, f) != 2 || tag[0] != 0x75) { u.error = "expected TC_ARRAY"; return false; }
         const bool full = tag[1] == 0x72;
-        const size_t rest = (full ? sizeof classDesc : sizeof classRef) - 1;
-        if (fread(tag + 2, 1, rest, f) != rest || memcmp(tag + 1, full ? classDesc : classRef, rest + 1) != 0) {
-            fclose(f); u.error = "unexpected array class (float[] expected)"; return false;
+        const size_t rest = (full ? sizeof kClassDesc : sizeof kClassRef) - 1;
+        if (fread(tag + 2, 1, rest, f) != rest || memcmp(tag + 1, full ? kClassDesc : kClassRef, rest + 1) != 0) {
+            u.error = "unexpected array class (float[] expected)";
+            return false;
         }
         unsigned char len[4];
-        if (fread(len, 1, 4, f) != 4 || (int32_t)be32(len) != u.n) { fclose(f); u.error = "array length differs from nbodies"; return false; }
-        u.arrays[a] = static_cast<float *>(malloc(sizeof(float) * (size_t)std::max(u.n, 1)));
-        std::string buf(4 * (size_t)u.n, '\0');
-        if (!u.arrays[a] || fread(&buf[0], 1, buf.size(), f) != buf.size()) { fclose(f); u.error = "short read"; return false; }
+        if (fread(len, 1, 4, f) != 4 || (int32_t)be32(len) != u.n) { u.error = "array length differs from nbodies"; return false; }
+        if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { u.error = "short read"; return false; }
+        u.arrays[a].resize((size_t)u.n);
         for (int32_t i = 0; i < u.n; ++i) {
-            const uint32_t v = be32(reinterpret_cast<const unsigned char *>(buf.data()) + 4 * (size_t)i);
+            const uint32_t v = be32(buf.data() + 4 * (size_t)i);
             memcpy(&u.arrays[a][i], &v, 4);
         }
     }
-    fclose(f);
     return true;
+}
+
+bool readUniverse(const char *path, bool headerOnly, int32_t expect, UniverseFile &u) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { u.error = std::string("cannot open ") + path; return false; }
+    bool ok = false;
+    try {
+        ok = readUniverseBody(f, headerOnly, expect, u);
+    } catch (const std::exception &) {  // bad_alloc / length_error must not cross the C boundary
+        u.error = "out of host memory while reading the universe file";
+    }
+    fclose(f);
+    return ok;
 }
 }  // namespace
 
 int bh_universe_file_bodies(const char *path, int32_t *nbodies) {
     if (!path || !nbodies) return BH_ERR_ARG;
     UniverseFile u;
-    if (!readUniverse(path, true, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
+    if (!readUniverse(path, true, 0, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
     *nbodies = u.n;
     return BH_OK;
 }
@@ -780,11 +1020,50 @@ int bh_upload_universe_file(bh_sim *sim, const char *path) {
     BH_ENTER(sim);
     if (!path) return fail(s, BH_ERR_ARG, "path is NULL");
     UniverseFile u;
-    if (!readUniverse(path, false, u)) return fail(s, BH_ERR_ARG, "%s", u.error.c_str());
-    if (u.n != s->n)  // SerializedUniverseGenerator.java:41-42 IllegalStateException
-        return fail(s, BH_ERR_ARG, "invalid amount of bodies for serialized universe (%d in the file, %d in the simulation)", u.n, s->n);
-    const float *src[7] = {u.arrays[0], u.arrays[1], u.arrays[2], u.arrays[3], u.arrays[4], u.arrays[5], u.arrays[6]};
+    if (!readUniverse(path, false, s->n, u)) return fail(s, BH_ERR_ARG, "%s", u.error.c_str());
+    const float *src[7];
+    for (int a = 0; a < 7; ++a) src[a] = u.arrays[a].data();
     return uploadImpl(s, src, cudaMemcpyHostToDevice);
+}
+
+int bh_write_universe_file(bh_sim *sim, const char *path) {
+    BH_ENTER(sim);
+    if (!path) return fail(s, BH_ERR_ARG, "path is NULL");
+    const size_t n = s->n;
+    int rc = ensureStaging(s, sizeof(float) * 7 * n);
+    if (rc) return rc;
+    bh::export_universe_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], static_cast<float *>(s->staging), s->n);
+    BH_CUDA(s, cudaGetLastError());
+    try {
+        std::vector<float> host(7 * n);
+        BH_CUDA(s, cudaMemcpyAsync(host.data(), s->staging, sizeof(float) * 7 * n, cudaMemcpyDeviceToHost, s->stream));
+        BH_CUDA(s, cudaStreamSynchronize(s->stream));
+        FILE *f = fopen(path, "wb");
+        if (!f) return fail(s, BH_ERR_ARG, "cannot create %s", path);
+        std::vector<unsigned char> buf(4 * n);
+        unsigned char word[4];
+        bool ok = fwrite(kMagic, 1, 6, f) == 6;
+        putBe32(word, (uint32_t)s->n);
+        ok = ok && fwrite(word, 1, 4, f) == 4;
+        for (int a = 0; a < 7 && ok; ++a) {  // UniverseSerializer.java:27-33: x, y, z, vx, vy, vz, mass
+            const unsigned char tcArray = 0x75;
+            ok = fwrite(&tcArray, 1, 1, f) == 1;
+            if (a == 0) ok = ok && fwrite(kClassDesc, 1, sizeof kClassDesc, f) == sizeof kClassDesc;
+            else ok = ok && fwrite(kClassRef, 1, sizeof kClassRef, f) == sizeof kClassRef;
+            ok = ok && fwrite(word, 1, 4, f) == 4;
+            for (size_t i = 0; i < n; ++i) {
+                uint32_t v;
+                memcpy(&v, &host[a * n + i], 4);
+                putBe32(buf.data() + 4 * i, v);
+            }
+            ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+        }
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) return fail(s, BH_ERR_ARG, "short write to %s", path);
+    } catch (const std::exception &) {
+        return fail(s, BH_ERR_ALLOC, "out of host memory while writing the universe file");
+    }
+    return BH_OK;
 }
 
 int bh_measure_fp32_peak(int32_t device, double *tflops) {

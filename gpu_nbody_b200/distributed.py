@@ -5,22 +5,28 @@ this is the one natural shard of its step (DESIGN.md "Multi-GPU"):
 
   every rank   bounding box -> build tree -> summarise -> sort   (replicated, identical trees)
   rank p       force walk for the sorted slots [first_p, first_p + count_p)
-  all ranks    all-gather of the sorted-order acceleration slices (NCCL over NVLink)
-  every rank   velocity correction + integrate for all bodies      (replicated, 68 B/body of HBM)
+  all ranks    all-gather of the sorted-order acceleration slices (16 B per body over NVLink)
+  every rank   velocity correction + integrate + reorder for all bodies (replicated, one fused pass)
 
 Slices are equal-sized multiples of 32 sorted slots, so vote groups are exactly
-those of the single-GPU run and the all-gather is in place.  Two transports for
-the all-gather: NCCL (`all_gather_into_tensor`), or -- `p2p=True` -- fused into
-the force kernel: every rank's acceleration buffer is mapped into every other
-rank (CUDA IPC over NVLink) and the walk's epilogue stores each result straight
-into all of them, so the transfer overlaps the walk; one 1-element NCCL
-all-reduce on the stream is the cross-rank barrier before the buffer is read.  What crosses NVLink
-is 16 B per body per step (float4 acceleration); positions never travel because
-the integrate is replicated and bit-deterministic.
+those of the single-GPU run and the all-gather is in place.  Two transports:
+
+* `p2p=True` (default in bench.py) -- the all-gather is fused into the force
+  kernel: every rank's acceleration buffer is mapped into every other rank
+  (CUDA IPC over NVLink) and the walk's epilogue stores each result straight
+  into all of them, so the transfer overlaps the walk.  The cross-rank barrier
+  before the buffer is read is a device kernel on flags in the same mapped
+  allocation, so the whole sliced step is inside the library (`bh_set_slice` +
+  `bh_step_async`: one CUDA graph per step, no host or NCCL call per step).
+* NCCL (`all_gather_into_tensor`) between `bh_calculate_force_slice` and
+  `bh_finish_async`; also the fallback when peer mapping fails on any rank.
+
+What crosses NVLink is 16 B per body per step (float4 acceleration); positions
+never travel because the finish pass is replicated and bit-deterministic.
 
 `engine` is anything with the stage methods below (the CUDA simulation in
-production; the CPU oracle in the world_size-2 gloo tests), `gather` performs
-the all-gather on the engine's sorted-order acceleration buffer.
+production; the CPU oracle in the world_size-2 gloo tests), the all-gather runs
+on the engine's sorted-order acceleration buffer.
 """
 from __future__ import annotations
 
@@ -75,7 +81,6 @@ class CudaSliceEngine:
     def connect_peers(self, rank, world_size, group=None):
         """Exchange the CUDA IPC handles of the acceleration buffers (host side, once)."""
         import ctypes as C
-        import torch
         import torch.distributed as dist
         mine = C.create_string_buffer(64)
         self._rc(self.lib.bh_ipc_export(self.h, mine))
@@ -83,20 +88,22 @@ class CudaSliceEngine:
         dist.all_gather_object(handles, mine.raw, group=group)
         blob = C.create_string_buffer(b"".join(handles), 64 * world_size)
         self._rc(self.lib.bh_ipc_set_peers(self.h, world_size, rank, blob))
-        self._flag = torch.zeros(1, device=self.device)
-        self._group = group
+
+    def disconnect_peers(self):
+        self._rc(self.lib.bh_ipc_clear_peers(self.h))
+
+    def set_slice(self, first, count):
+        self._rc(self.lib.bh_set_slice(self.h, first, count))
+
+    def step_fused_async(self, nsteps):
+        """The whole sliced step inside the library (peer stores + device barrier, one CUDA graph per step)."""
+        self._rc(self.lib.bh_step_async(self.h, nsteps))
 
     def force_slice(self, first, count):
-        if self.p2p:
-            import torch.distributed as dist
-            self._rc(self.lib.bh_calculate_force_slice_p2p(self.h, first, count))
-            dist.all_reduce(self._flag, group=self._group)  # stream-ordered barrier: every rank's stores have landed
-        else:
-            self._rc(self.lib.bh_calculate_force_slice(self.h, first, count))
+        self._rc(self.lib.bh_calculate_force_slice(self.h, first, count))
 
     def apply_and_integrate(self):
-        self._rc(self.lib.bh_apply_acceleration(self.h))
-        self._rc(self.lib.bh_stage_async(self.h, 5))
+        self._rc(self.lib.bh_finish_async(self.h))
 
     def check(self):
         self._rc(self.lib.bh_check(self.h))
@@ -111,6 +118,7 @@ class DistributedBarnesHutSimulation:
         if self.chunk * world_size > engine.acc_sorted.shape[0]:
             raise ValueError("acceleration buffer too small for %d ranks" % world_size)
         self.fused = bool(getattr(engine, "p2p", False)) and world_size > 1
+        self.peer_error = None
         if self.fused:
             # every rank must take the same path: agree on whether peer mapping worked everywhere
             import torch
@@ -125,16 +133,24 @@ class DistributedBarnesHutSimulation:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             self.fused = bool(flag.item())
             engine.p2p = self.fused
+            if self.fused:
+                engine.set_slice(*self.bounds[rank])
+            else:
+                # ranks that did map their peers must unmap them: all ranks run the same (NCCL) protocol
+                engine.disconnect_peers()
 
     def step_async(self, nsteps: int = 1):
-        import torch.distributed as dist
+        if self.fused:
+            self.engine.step_fused_async(nsteps)
+            return
         first, count = self.bounds[self.rank]
         full = self.engine.acc_sorted[: self.chunk * self.world_size]
         mine = full[self.rank * self.chunk:(self.rank + 1) * self.chunk]
         for _ in range(nsteps):
             self.engine.tree_stages()
             self.engine.force_slice(first, count)
-            if self.world_size > 1 and not self.fused:
+            if self.world_size > 1:
+                import torch.distributed as dist
                 dist.all_gather_into_tensor(full, mine, group=self.group)
             self.engine.apply_and_integrate()
 

@@ -179,6 +179,23 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
         k = {"cubic": 0, "plummer": 1, "disk": 2}[kind]
         self._check(self._lib.bh_generate_universe(self._sim, k, int(seed), float(p0), float(p1), float(p2)))
 
+    def setForceDeepWalk(self, on=True):
+        """Validation: always run the deep-tree fallback kernel of the force walk."""
+        self._check(self._lib.bh_set_force_deep_walk(self._sim, int(on)))
+
+    def setVertexBuffers(self, pos4_device_ptr, vel4_device_ptr):
+        """GL_INTEROP (GPUBH:230-246,265-266): device pointers of two float4[nbodies] buffers (e.g. CUDA-mapped GL
+        vertex buffers) that every step's finish pass fills; (0, 0) switches it off."""
+        self._check(self._lib.bh_set_vertex_buffers(self._sim, C.c_void_p(pos4_device_ptr or None), C.c_void_p(vel4_device_ptr or None)))
+
+    def copyVerticesDevice(self, pos4_device_ptr, vel4_device_ptr):
+        """copyvertices.cl:8-17 into device buffers, asynchronously on the simulation's stream."""
+        self._check(self._lib.bh_copy_vertices_device(self._sim, C.c_void_p(pos4_device_ptr or None), C.c_void_p(vel4_device_ptr or None)))
+
+    def writeUniverseFile(self, path):
+        """UniverseSerializer.serialize (UniverseSerializer.java:25-34) of the current state, natively."""
+        self._check(self._lib.bh_write_universe_file(self._sim, str(path).encode()))
+
     def uploadUniverseFile(self, path):
         """SerializedUniverseGenerator without a JVM: read a .universe file natively and upload it."""
         self._check(self._lib.bh_upload_universe_file(self._sim, str(path).encode()))

@@ -10,7 +10,15 @@
  * bh_last_error) and a positive value when the device `error` buffer is set
  * (1 = cell pool exhausted or tree deeper than 64 levels, exactly the two
  * conditions of buildtree.cl:112-119 and calculateforce.cl:69-73;
- * 2 = a device-side wait exceeded its spin budget).
+ * 2 = a device-side wait exceeded its spin budget; 3 = the multi-GPU peer
+ * barrier timed out).
+ *
+ * Residency: the sort stage (kernels/nbody/sort.cl) waits, thread on thread, for
+ * the `start` value of a cell's parent, as the reference does.  It is launched
+ * cooperatively (cudaLaunchCooperativeKernel): all its CTAs are co-resident or
+ * the launch waits for the device, so work on other streams of the same
+ * device (another bh_sim, NCCL, MPS clients) can delay it but not starve it.
+ * Every device-side wait is bounded (2^24 polls, then error 2), never a hang.
  *
  * Threading: a bh_sim is thread-compatible, not thread-safe (the reference is
  * driven from one JOGL animator thread, NBodyVisualizer.java:460-470).  Every
@@ -72,6 +80,9 @@ typedef struct bh_stats_t {
     int64_t stage_launches[BH_NUM_STAGES]; /* kernel launches per stage since reset */
     int64_t interactions;     /* (body,node) force evaluations of the last counted force call */
     int64_t opens;            /* (body,cell) opening tests that pushed, same call */
+    double barrier_ms;        /* summed CUDA-event time of the multi-GPU peer barrier (ABI >= 2) */
+    int32_t deep_walk;        /* 1 = the last force stage was redone by the deep-tree walk kernel (ABI >= 2) */
+    int32_t reserved;
 } bh_stats_t;
 
 /* GPUBH.init():111-151 -- context, node-pool sizing (219-227), buffer creation (153-181).
@@ -94,9 +105,13 @@ int bh_use_private_stream(bh_sim *sim);
 int bh_set_profiling(bh_sim *sim, int32_t on);
 /* 1 = count interactions/opens in the next force calls (slower kernel variant); 0 = off. */
 int bh_set_counting(bh_sim *sim, int32_t on);
-/* Order in which build_tree inserts bodies: 0 = index order, 1 = previous step's
- * sorted (DFS / Morton-like) order.  The resulting tree is identical. */
+/* Body storage / insertion order: 1 (default) = after every step the bodies are physically stored in
+ * that step's sorted (DFS / Morton-like) order, which is the next build's insertion order (coalesced
+ * loads); 0 = bodies stay in upload order.  Results and everything bh_read returns are identical. */
 int bh_set_insertion_order(bh_sim *sim, int32_t mode);
+/* Debug/validation: 1 = always run the deep-tree fallback of the force walk (the kernel that takes over
+ * when a tree is too deep for the fast walk's shared-memory stacks); 0 = automatic (default). */
+int bh_set_force_deep_walk(bh_sim *sim, int32_t on);
 /* 1 (default) = bh_step replays one captured CUDA graph per step (six kernels, fixed arguments); 0 = six launches. */
 int bh_set_graph(bh_sim *sim, int32_t on);
 
@@ -129,20 +144,30 @@ int bh_check(bh_sim *sim); /* sync + error buffer */
  * bh_calculate_force_slice walks the tree for sorted slots [first, first+count)
  * (first a multiple of vote_width) and stores float4 {ax,ay,az,0} per slot into
  * the sorted-order acceleration buffer; after the caller has all-gathered that
- * buffer across ranks, bh_apply_acceleration performs the velocity correction
- * and acc store of calculateforce.cl:174-185 for all N bodies.  Both async. */
+ * buffer across ranks, bh_finish_async performs the velocity correction and acc
+ * store of calculateforce.cl:174-185 and the integrate of integrate.cl for all N
+ * bodies in one pass (bh_apply_acceleration: the velocity correction alone).  All async. */
 int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count);
 int bh_apply_acceleration(bh_sim *sim);
+int bh_finish_async(bh_sim *sim);
 void *bh_acc_sorted_device_ptr(bh_sim *sim); /* float4[N + 2048] in device memory (slack for equal, aligned slices) */
-/* Peer-memory variant (one process per GPU, one node): the all-gather is fused into the force kernel.
+/* Peer-memory variant (one process per GPU, one node): the all-gather is fused into the force kernel and the
+ * whole sliced step runs inside bh_step / bh_step_async (one CUDA graph per step, no host or NCCL call in it).
  * Every rank exports its acceleration buffer (bh_ipc_export: 64-byte CUDA IPC handle), the host exchanges
- * the handles (any transport) and hands all of them to bh_ipc_set_peers; bh_calculate_force_slice_p2p then
- * stores each slot's result into the own buffer and, over NVLink, into every peer's.  The caller must put
- * one cross-rank barrier on the stream (e.g. a 1-element NCCL all-reduce) between this call and
- * bh_apply_acceleration; the buffer is double-buffered per step, so no second barrier is needed. */
+ * the handles (any transport) and hands all of them to bh_ipc_set_peers; bh_set_slice names the rank's
+ * slice of the sorted order.  From then on the step's force stage walks the slice and stores each slot's
+ * result into the own buffer and, over NVLink, into every peer's; a device-side barrier (flags in the same
+ * peer-mapped allocation, release/acquire at system scope) separates it from the finish pass, which every
+ * rank runs over all N bodies.  The buffer is double-buffered per step, so one barrier per step is enough.
+ * All ranks must call bh_step the same number of times.  bh_ipc_clear_peers unmaps the peers and returns to
+ * the single-GPU step (call it on every rank if bh_ipc_set_peers failed on any).
+ * bh_calculate_force_slice_p2p / bh_peer_barrier are the same two pieces as single async calls. */
 int bh_ipc_export(bh_sim *sim, void *handle64);
 int bh_ipc_set_peers(bh_sim *sim, int32_t nranks, int32_t my_rank, const void *handles /* nranks x 64 bytes */);
+int bh_ipc_clear_peers(bh_sim *sim);
+int bh_set_slice(bh_sim *sim, int32_t first, int32_t count);
 int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count);
+int bh_peer_barrier(bh_sim *sim);
 /* Async single stages for callers that sequence their own stream. */
 int bh_stage_async(bh_sim *sim, int32_t stage /* enum bh_stage */);
 
@@ -155,6 +180,13 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which);
 /* kernels/nbody/copyvertices.cl:8-17 with host destinations: pos4[i] = {x,y,z,1},
  * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
 int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
+/* The same with DEVICE destinations (float4[nbodies] each) -- what a CUDA-mapped OpenGL vertex buffer is
+ * (cudaGraphicsResourceGetMappedPointer; GPUBH:230-246 createFromGLBuffer + :253-256 acquire): async on the
+ * simulation's stream, no host staging. */
+int bh_copy_vertices_device(bh_sim *sim, void *pos4_device, void *vel4_device);
+/* GL_INTEROP mode of GPUBH.step() (:265-266): from now on every step's finish pass also writes the float4
+ * vertices into these device buffers (fused, no extra kernel); NULL, NULL switches it off. */
+int bh_set_vertex_buffers(bh_sim *sim, void *pos4_device, void *vel4_device);
 
 /* Seeded universe generators on the device (the reference's universe generators draw from the unseeded
  * Math.random() on the host and upload): Philox4x32-10, one subsequence per body; resets the other buffers
@@ -176,6 +208,9 @@ int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out);
  * fails like the reference when the body count differs from the simulation's. */
 int bh_universe_file_bodies(const char *path, int32_t *nbodies);
 int bh_upload_universe_file(bh_sim *sim, const char *path);
+/* UniverseSerializer.serialize (universe/serialize/UniverseSerializer.java:25-34) for the simulation's CURRENT
+ * state, host numbering: a state dump every SerializedUniverseGenerator (Java or bh_upload_universe_file) reads. */
+int bh_write_universe_file(bh_sim *sim, const char *path);
 
 int bh_stats(bh_sim *sim, bh_stats_t *out);
 int bh_reset_stats(bh_sim *sim);

@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
     SYM(bh_create) SYM(bh_destroy) SYM(bh_last_error) SYM(bh_number_of_nodes) SYM(bh_abi_version) SYM(bh_upload) SYM(bh_step) SYM(bh_read)
     bh_stats_t_fn p_bh_stats = (bh_stats_t_fn)dlsym(lib, "bh_stats");
     if (!p_bh_stats) return 2;
-    if (p_bh_abi_version() != 1) return 3;
+    if (p_bh_abi_version() != 2) return 3;
     if (p_bh_number_of_nodes(32768) != 65536 || p_bh_number_of_nodes(1) != 16384) return 4;  /* GPUBH:219-227 */
     const int gpu = argc > 1 && strcmp(argv[1], "gpu") == 0;
     bh_sim *sim = NULL;

@@ -71,7 +71,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(declared) == set(lib._protos), set(declared) ^ set(lib._protos)
-    assert lib.bh_abi_version() == 1
+    assert lib.bh_abi_version() == 2
 
 
 def test_no_cuda_device_fails_loudly():
