@@ -204,7 +204,7 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = {k: (v / st["steps_timed"] if st["steps_timed"] else None) for k, v in st["stage_ms"].items()}
 
     # ---- e2e: host buffers in, host buffers out, every step ----
-    if args.gpu_gen:
+    if args.gpu_gen or args.no_e2e:
         if rank == 0:
             value = n * K / (ms_total * 1e-3)
             print(json.dumps({"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -325,6 +325,7 @@ def main():
     ap.add_argument("--dist", default="plummer", choices=["plummer", "uniform", "disks"])
     ap.add_argument("--seed", type=int, default=43)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     ap.add_argument("--gpu-gen", action="store_true", help="draw the universe on the device (memory-sized runs; skips the e2e and cpu legs)")
     ap.add_argument("--nccl-allgather", action="store_true", help="multi-GPU: NCCL all-gather instead of the peer-memory stores fused into the force kernel")
     args = ap.parse_args()

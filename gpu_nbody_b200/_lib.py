@@ -113,6 +113,7 @@ def load():
         "bh_generate_universe": (C.c_int, [p, i32, C.c_uint64, f32, f32, f32]),
         "bh_universe_file_bodies": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
         "bh_upload_universe_file": (C.c_int, [p, C.c_char_p]),
+        "bh_read_universe_file": (C.c_int, [C.c_char_p, i32] + [p] * 7),
         "bh_reset_stats": (C.c_int, [p]),
         "bh_number_of_bodies": (i32, [p]),
         "bh_number_of_nodes": (i32, [i32]),

@@ -58,7 +58,7 @@ struct Scalars {
     int maxDepth;     // init 1, running max (buildtree.cl:199)
     int bottom;
     int error;
-    int deep;         // the walk ran out of shared-memory stack: deep_walk_kernel redoes the stage
+    int deep;         // (unused since the walk spills its stacks)
     int rootEntry;    // walk entry of the root cell (written by summarise)
     unsigned long long interactions;
     unsigned long long opens;
@@ -616,150 +616,233 @@ struct PeerBuffers {
 };
 
 // ---- 5a. the walk: one private work list per vote group ---------------------------------------------------------
-// Every vote group (8 lanes) keeps, in shared memory, a stack of cells it has decided to open and a LIFO of
-// child records waiting to be tested.  A warp-wide step tests ONE queued child per group -- four different
-// children, each against its own group's 16 bodies (LDS.128 with one address per quarter warp) -- so no lane
-// ever works on a node its group does not need (a shared walk of the four groups' union costs ~25 % more
+// A lane carries FOUR consecutive sorted bodies (two packed pairs), four lanes are one 16-body vote group, a
+// warp works on eight groups at a time.  Every group keeps, in shared memory, a stack of cells it has decided
+// to open and a LIFO of child records waiting to be tested.  A warp-wide step tests ONE queued child per group
+// -- eight different children, each against its own group's 16 bodies (LDS.128 with one address per group) --
+// so no lane ever works on a node its group does not need (a shared walk of the groups' union costs ~25 % more
 // child tests), and the per-cell bookkeeping of a stack walk (pop, row fetch, loop control: a third of the
-// issue slots of a pop-per-cell design) is paid once per ~25 children: when a group's queue runs low its
-// lanes pop up to eight cells at once (one per lane; the number of children is part of the stack entry, so
-// the space is assigned by an 8-lane prefix sum without touching memory) and LDGSTS copies the children's
-// records {x,y,z,m} + {threshold, entry} from the cells' walk records straight into the queue.
-// Per child: LDS.128 + LDS.64, 7 packed fp32 (distance), 2 FSETP + VOTE + LOP3 (the group's vote, :145),
-// 2 MUFU.RSQ, 6 packed fp32 (the interaction, zero mass if the group opens the cell), predicated push.
-// If a group's cell stack cannot take another batch (trees deeper than ~25 levels at theta = 0.5) the kernel
-// raises sc->deep and deep_walk_kernel, launched right behind it, redoes the stage with its 64-level stack.
+// issue slots of a pop-per-cell design) is paid once per ~20 children: when any group's queue runs low, every
+// group tops its queue up, popping cells from its stack and copying their walk records -- children {x,y,z,m}
+// and {threshold, entry}, one 128-byte and one 64-byte line per cell -- with LDGSTS straight into the queue.
+// Per child (128 interactions): LDS.128 + LDS.32, 14 packed fp32 (distances), 3 FMNMX + FSETP + VOTE + LOP3
+// (the group's vote, :145), 4 MUFU.RSQ, 12 packed fp32 (the interactions; zero mass if the group opens the
+// cell), predicated push: 26 of ~42 issue slots are packed fp32, so the kernel is bound by the fp32 pipe,
+// not by issue.  CTAs are persistent: a group slot whose walk is finished writes its accelerations and takes
+// the next group of the CTA's current chunk (chunks of 2^chunkShift groups are dealt round-robin to the CTAs), so a warp
+// never waits for its slowest group.
+// A group's cell stack holds 128 entries in shared memory; in deep trees (7 open siblings per level) its bottom
+// half is spilled to a per-slot global buffer and comes back when the shared part runs dry, so any tree the
+// reference accepts (64 levels) is walked by this kernel.
 constexpr int kWalkThreads = 128;
-constexpr int kWalkBodies = 2 * kWalkThreads;  // per CTA
-constexpr int kWalkBatch = 6;    // children tested per group between two looks at the queue
-constexpr int kWalkQCap = 32;    // queued children per group
-constexpr int kWalkSCap = 160;   // stacked cells per group
+constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kWalkGroups = 8;        // vote groups per warp (4 lanes x 4 bodies)
+constexpr int kWalkBatch = 6;         // children tested per group between two looks at the queue
+constexpr int kWalkQCap = 26;         // queued children per group
+constexpr int kWalkSlots = kWalkBatch + kWalkQCap;  // the lowest kWalkBatch slots hold zero-mass dummies
+constexpr int kWalkSCap = 128;        // stacked cells per group in shared memory
+constexpr int kWalkSpill = 64;        // entries moved to / from the global spill buffer at a time
+constexpr int kWalkSpillCap = 1024;   // spill entries per group slot (7 * 64 + 8 would do)
+constexpr int kWalkRefillCells = 6;   // cells a group pops per refill, at most
+constexpr int kWalkCtasPerSM = 5;
+
+struct WalkShared {
+    // +1 padding: the groups' arrays start 4 (2, 1) banks apart, so equal indices in different groups do not collide
+    int stk[kWalkWarps][kWalkGroups][kWalkSCap + 1];
+    float4 rec[kWalkWarps][kWalkGroups][kWalkSlots + 1];
+    int2 meta[kWalkWarps][kWalkGroups][kWalkSlots + 1];
+    int next;  // next group of the CTA's schedule
+};
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
-                                                            const int2 *__restrict__ ometa, const int *__restrict__ perm,
-                                                            const PeerBuffers dst, Scalars *sc, int n, int first, int cnt,
-                                                            float eps, int forceDeep) {
-    constexpr int kWarps = kWalkThreads / 32;
-    constexpr int kSlots = kWalkBatch + kWalkQCap;  // the lowest kWalkBatch slots hold zero-mass dummies
-    __shared__ int stk[kWarps][4][kWalkSCap];
-    __shared__ float4 qrec[kWarps][4][kSlots];
-    __shared__ int2 qmeta[kWarps][4][kSlots];
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
+                                                                            const int2 *__restrict__ ometa, const int *__restrict__ perm,
+                                                                            const PeerBuffers dst, Scalars *sc, int *__restrict__ spill, int n,
+                                                                            int first, int cnt, float eps, int chunkShift) {
+    __shared__ WalkShared sh;
     if (sc->error != 0) return;
     if (sc->maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
         return;
     }
-    if (forceDeep) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) sc->deep = 1;
-        return;
-    }
-    if (*reinterpret_cast<volatile int *>(&sc->deep) != 0) return;  // another CTA already gave up: the stage is redone anyway
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 3, j = lane & 7;
+    const int g = lane >> 2, l = lane & 3;
+    if (threadIdx.x == 0) sh.next = kWalkWarps * kWalkGroups;
+    if (l == 0) {
+#pragma unroll
+        for (int i = 0; i < kWalkBatch; ++i) {  // dummies: zero mass, always accepted, never counted
+            sh.rec[warp][g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sh.meta[warp][g][i] = make_int2(__float_as_int(-1.0f), -2);
+        }
+    }
+    __syncthreads();
     const int end = first + cnt;
-    const int base = first + (blockIdx.x * kWarps + warp) * 64;
-    // lane l carries sorted slots base+2l and base+2l+1 (same vote group)
-    const int k0 = base + 2 * lane;
-    const int nact = min(2, max(0, end - k0));  // bodies of this lane that exist
-    unsigned gm = 0xffu << (8 * g);             // lanes of my group
-    asm volatile("" : "+r"(gm));                // keep it in a register (ptxas would rematerialise it per vote)
-    // a slot past the end borrows the position of the group's first body: its vote then equals that body's
-    const int kg = base + 16 * g;
-    const int s0 = (nact > 0) ? k0 : max(0, min(kg, end - 1)), s1 = (nact > 1) ? k0 + 1 : s0;
-    const float4 p0 = body4[perm ? perm[s0] : s0], p1 = body4[perm ? perm[s1] : s1];  // perm == nullptr: bodies lie in tree order
-    const float2 npx = make_float2(-p0.x, -p1.x), npy = make_float2(-p0.y, -p1.y), npz = make_float2(-p0.z, -p1.z);
+    const int totalGroups = (cnt + 15) >> 4;
+    const int rootEntry = sc->rootEntry;
+    const size_t phase = (size_t)(sc->step & 1) * dst.phaseStride;
+    unsigned gm = 0xfu << (lane & ~3);  // lanes of my group
+    asm volatile("" : "+r"(gm));        // keep it in a register (ptxas would rematerialise it per vote)
     const float2 eps2 = make_float2(eps, eps);
-    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
-    unsigned long long nInter = 0, nOpen = 0;
     // shared memory through 32-bit shared-window addresses kept in registers
-    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(&stk[warp][g][0]);
+    const unsigned stkBase = (unsigned)__cvta_generic_to_shared(&sh.stk[warp][g][0]);
     const unsigned stkLimit = stkBase + 4u * (kWalkSCap - kWalkBatch);  // a batch pushes at most kWalkBatch cells
-    const unsigned qBase = (unsigned)__cvta_generic_to_shared(&qrec[warp][g][kWalkBatch]);
-    const unsigned mBase = (unsigned)__cvta_generic_to_shared(&qmeta[warp][g][kWalkBatch]);
-    if (j < kWalkBatch) {  // dummies: zero mass, always accepted, never counted
-        qrec[warp][g][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qmeta[warp][g][j] = make_int2(__float_as_int(-1.0f), -2);
-    }
+    const unsigned qBase = (unsigned)__cvta_generic_to_shared(&sh.rec[warp][g][kWalkBatch]);
+    const unsigned mBase = (unsigned)__cvta_generic_to_shared(&sh.meta[warp][g][kWalkBatch]);
+    const unsigned nextAddr = (unsigned)__cvta_generic_to_shared(&sh.next);
     unsigned stkTop = stkBase, qTop = qBase, mTop = mBase;  // one past the top entry; the same in all lanes of a group
-    const bool groupActive = (__ballot_sync(kFull, nact > 0) & gm) != 0u;
-    if (groupActive) {
-        sts_s32(stkTop, sc->rootEntry);
-        stkTop += 4;
-    }
-    __syncwarp();
+    int *const mySpill = spill + ((size_t)(blockIdx.x * kWalkWarps + warp) * kWalkGroups + g) * kWalkSpillCap;
+    int spilled = 0;  // entries of my group's stack that live in the spill buffer (below the shared-memory part)
+    // the group this slot works on
+    int idx = warp * kWalkGroups + g;  // position in the CTA's schedule
+    bool active = false;               // the slot has a group
+    bool fetch = true;                 // the slot wants the group at `idx`
+    int k0 = 0, nact = 0;
+    float2 npxA = make_float2(0.f, 0.f), npyA = npxA, npzA = npxA, npxB = npxA, npyB = npxA, npzB = npxA;
+    float2 axA = npxA, ayA = npxA, azA = npxA, axB = npxA, ayB = npxA, azB = npxA;
+    unsigned long long nInter = 0, nOpen = 0;
     for (;;) {
-        const bool low = qTop < qBase + 16u * kWalkBatch;  // fewer than a batch of real children queued
-        const bool need = low && stkTop != stkBase;
-        if (__any_sync(kFull, need)) {
-            // ---- refill: lane j of a group in need pops the j-th cell from the top of its stack ------------------
-            const int avail = (int)(stkTop - stkBase) >> 2;
-            int e = 0, c = 0;
-            if (need && j < avail) {
-                e = lds_s32(stkTop - 4u * (unsigned)(j + 1));
-                c = ((e >> 27) & 7) + 1;  // children of my cell
-            }
-            int incl = c;  // inclusive prefix sum within the group
+        // ---- group slots: finished walks write their accelerations and take the next group ---------------------
+        const bool finished = active && stkTop == stkBase && qTop == qBase && spilled == 0;
+        if (__any_sync(kFull, finished || fetch)) {
+            if (finished) {
+                const float4 a[4] = {make_float4(axA.x, ayA.x, azA.x, 0.f), make_float4(axA.y, ayA.y, azA.y, 0.f),
+                                     make_float4(axB.x, ayB.x, azB.x, 0.f), make_float4(axB.y, ayB.y, azB.y, 0.f)};
+                for (int r = 0; r < dst.count; ++r) {  // own buffer, then the peers' (NVLink stores)
+                    float4 *out = dst.buf[r] + phase + k0;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, o, 8);
-                if (j >= o) incl += v;
+                    for (int t = 0; t < 4; ++t)
+                        if (t < nact) out[t] = a[t];
+                }
+                int nx = 0;
+                if (l == 0) asm volatile("atom.shared.add.s32 %0, [%1], 1;" : "=r"(nx) : "r"(nextAddr) : "memory");
+                idx = __shfl_sync(gm, nx, lane & ~3);
             }
-            const int freeSlots = kWalkQCap - ((int)(qTop - qBase) >> 4);
-            const bool take = c > 0 && incl <= freeSlots;  // true for a prefix of the lanes (incl grows with j)
-            const int taken = __popc(__ballot_sync(kFull, take) & gm);
-            const int total = __shfl_sync(kFull, incl, max(taken - 1, 0), 8);  // children of the cells taken
-            if (take) {
-                const int rel = e & kEntryMask;
-                const float4 *src = octet + (size_t)rel * 8;
-                const int2 *msrc = ometa + (size_t)rel * 8;
-                const unsigned d = qTop + 16u * (unsigned)(incl - c), md = mTop + 8u * (unsigned)(incl - c);
+            if (finished || fetch) {
+                fetch = false;
+                // chunks of 2^chunkShift consecutive groups are dealt round-robin to the CTAs
+                const long long grp = (((long long)blockIdx.x + (long long)(idx >> chunkShift) * gridDim.x) << chunkShift) + (idx & ((1 << chunkShift) - 1));
+                active = grp < totalGroups;
+                if (active) {
+                    const int gfirst = first + (int)grp * 16;  // the group's first sorted slot (exists)
+                    k0 = gfirst + 4 * l;
+                    nact = min(4, max(0, end - k0));
+                    // a slot past the end borrows the position of the group's first body: its vote then equals that body's
+                    float4 p[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < c) {
-                        cp_async16(d + 16u * k, src + k);
-                        cp_async8(md + 8u * k, msrc + k);
+                    for (int t = 0; t < 4; ++t) {
+                        const int s = t < nact ? k0 + t : gfirst;
+                        p[t] = body4[perm ? perm[s] : s];  // perm == nullptr: bodies lie in tree order
                     }
+                    npxA = make_float2(-p[0].x, -p[1].x); npyA = make_float2(-p[0].y, -p[1].y); npzA = make_float2(-p[0].z, -p[1].z);
+                    npxB = make_float2(-p[2].x, -p[3].x); npyB = make_float2(-p[2].y, -p[3].y); npzB = make_float2(-p[2].z, -p[3].z);
+                    axA = ayA = azA = axB = ayB = azB = make_float2(0.f, 0.f);
+                    sts_s32(stkBase, rootEntry);
+                    stkTop = stkBase + 4;
+                    qTop = qBase;
+                    mTop = mBase;
+                } else {
+                    nact = 0;
+                }
             }
-            if (taken > 0) {
-                stkTop -= 4u * (unsigned)taken;
-                qTop += 16u * (unsigned)total;
-                mTop += 8u * (unsigned)total;
+            if (__all_sync(kFull, !active)) break;
+        }
+        // ---- refill: when any group is short of a batch, every group tops its queue up --------------------------
+        if (__any_sync(kFull, qTop < qBase + 16u * kWalkBatch && (stkTop != stkBase || spilled != 0))) {
+            if (__any_sync(kFull, stkTop == stkBase && spilled != 0)) {  // (cold) a dry stack takes spilled entries back
+                if (stkTop == stkBase && spilled != 0) {
+                    const int take = min(spilled, kWalkSpill);
+                    spilled -= take;
+                    for (int t = l; t < take; t += 4) sts_s32(stkBase + 4u * (unsigned)t, mySpill[spilled + t]);
+                    stkTop = stkBase + 4u * (unsigned)take;
+                }
+                __syncwarp();
+            }
+            int room = kWalkQCap - ((int)(qTop - qBase) >> 4);
+            bool alive = active;
+#pragma unroll
+            for (int r = 0; r < kWalkRefillCells; ++r) {
+                alive = alive && stkTop != stkBase;
+                int e = 0;
+                if (alive) e = lds_s32(stkTop - 4u);
+                const int c = ((e >> 27) & 7) + 1;  // children of the cell on top of the stack
+                alive = alive && c <= room;
+                if (alive) {
+                    const int rel = e & kEntryMask;
+                    const float4 *src = octet + (size_t)rel * 8 + l;
+                    const int2 *msrc = ometa + (size_t)rel * 8 + l;
+                    const unsigned d = qTop + 16u * (unsigned)l, md = mTop + 8u * (unsigned)l;
+                    if (l < c) { cp_async16(d, src); cp_async8(md, msrc); }
+                    if (l + 4 < c) { cp_async16(d + 64u, src + 4); cp_async8(md + 32u, msrc + 4); }
+                    stkTop -= 4u;
+                    qTop += 16u * (unsigned)c;
+                    mTop += 8u * (unsigned)c;
+                    room -= c;
+                }
             }
             cp_async_wait_all();
             __syncwarp();
-        } else if (__all_sync(kFull, qTop == qBase)) {
-            break;  // every group: nothing queued, nothing stacked
         }
-        if (__any_sync(kFull, stkTop > stkLimit)) {  // no room for the pushes of another batch: leave it to the deep kernel
-            if (lane == 0) sc->deep = 1;
-            return;
-        }
-        // ---- one batch: the top kWalkBatch queued children of every group (dummies below a short queue) ----------
+        // ---- batches, back to back until some group must refill or has finished ---------------------------------
+        do {
+            if (__any_sync(kFull, stkTop > stkLimit)) {  // (cold) no room for the pushes of another batch: spill the bottom entries
+                if (stkTop > stkLimit) {
+                    if (spilled + kWalkSpill > kWalkSpillCap) {
+                        atomicCAS(&sc->error, 0, 2);  // cannot happen for trees of at most 64 levels
+                    } else {
+                        const int rest = ((int)(stkTop - stkBase) >> 2) - kWalkSpill;  // 58..64 entries stay
+                        int keep[kWalkSpill / 4];
 #pragma unroll
-        for (int i = 1; i <= kWalkBatch; ++i) {
-            const float4 c = lds_v4(qTop - 16u * i);
-            int thrBits, ent;
-            lds_v2(mTop - 8u * i, thrBits, ent);
-            const float thr = __int_as_float(thrBits);
-            BH_DIST(c, 0)
-            const bool far = !(r20.x < thr) && !(r20.y < thr);  // r^2 >= dq (a NaN never opens: no entry of a body is ever pushed)
-            const unsigned nearMask = __ballot_sync(kFull, !far);
-            const bool open = (nearMask & gm) != 0u;  // :145 work_group_all failed: my group opens the cell
-            force_accumulate(dx0, dy0, dz0, r20, open ? 0.0f : c.w, ax, ay, az);
-            if (open) {  // all lanes of the group store the same entry to the same address
-                sts_s32(stkTop, ent);
-                stkTop += 4;
+                        for (int t = 0; t < kWalkSpill / 4; ++t) {
+                            mySpill[spilled + l + 4 * t] = lds_s32(stkBase + 4u * (unsigned)(l + 4 * t));
+                            keep[t] = (l + 4 * t < rest) ? lds_s32(stkBase + 4u * (unsigned)(kWalkSpill + l + 4 * t)) : 0;
+                        }
+                        __syncwarp(gm);
+#pragma unroll
+                        for (int t = 0; t < kWalkSpill / 4; ++t)
+                            if (l + 4 * t < rest) sts_s32(stkBase + 4u * (unsigned)(l + 4 * t), keep[t]);
+                        spilled += kWalkSpill;
+                        stkTop -= 4u * kWalkSpill;
+                    }
+                }
+                __syncwarp();
             }
-            if (COUNT) {
-                if (open) nOpen += nact;
-                else if (ent != -2) nInter += nact;
+            // ---- one batch: the top kWalkBatch queued children of every group (dummies below a short queue) ----------
+#pragma unroll
+            for (int i = 1; i <= kWalkBatch; ++i) {
+                const float4 c = lds_v4(qTop - 16u * i);
+                const float thr = lds_f32(mTop - 8u * i);
+                const float2 cx2 = make_float2(c.x, c.x), cy2 = make_float2(c.y, c.y), cz2 = make_float2(c.z, c.z);
+                const float2 dxA = __fadd2_rn(cx2, npxA), dyA = __fadd2_rn(cy2, npyA), dzA = __fadd2_rn(cz2, npzA);  // c - p, exactly
+                const float2 dxB = __fadd2_rn(cx2, npxB), dyB = __fadd2_rn(cy2, npyB), dzB = __fadd2_rn(cz2, npzB);
+                const float2 r2A = __fadd2_rn(__ffma2_rn(dzA, dzA, __ffma2_rn(dyA, dyA, __fmul2_rn(dxA, dxA))), eps2);  // :138-143
+                const float2 r2B = __fadd2_rn(__ffma2_rn(dzB, dzB, __ffma2_rn(dyB, dyB, __fmul2_rn(dxB, dxB))), eps2);
+                const float rmin = fminf(fminf(r2A.x, r2A.y), fminf(r2B.x, r2B.y));
+                const bool far = !(rmin < thr);  // r^2 >= dq for the lane's four bodies (a NaN never opens: no entry of a body is ever pushed)
+                const unsigned nearMask = __ballot_sync(kFull, !far);
+                const bool open = (nearMask & gm) != 0u;  // :145 work_group_all failed: my group opens the cell
+                const float mw = open ? 0.0f : c.w;
+                const float2 mw2 = make_float2(mw, mw);
+                const float2 rinvA = make_float2(rsqrt_fast(r2A.x), rsqrt_fast(r2A.y)), rinvB = make_float2(rsqrt_fast(r2B.x), rsqrt_fast(r2B.y));
+                // :146-148 m r^-3; the mass (the only operand that waits for the vote) is multiplied in last
+                const float2 fA = __fmul2_rn(__fmul2_rn(__fmul2_rn(rinvA, rinvA), rinvA), mw2);
+                const float2 fB = __fmul2_rn(__fmul2_rn(__fmul2_rn(rinvB, rinvB), rinvB), mw2);
+                axA = __ffma2_rn(dxA, fA, axA); ayA = __ffma2_rn(dyA, fA, ayA); azA = __ffma2_rn(dzA, fA, azA);  // :149-151
+                axB = __ffma2_rn(dxB, fB, axB); ayB = __ffma2_rn(dyB, fB, ayB); azB = __ffma2_rn(dzB, fB, azB);
+                if (open) {  // all lanes of the group store the same entry to the same address
+                    sts_s32(stkTop, lds_s32(mTop - 8u * i + 4u));
+                    stkTop += 4;
+                }
+                if (COUNT) {
+                    if (open) nOpen += nact;
+                    else if (lds_s32(mTop - 8u * i + 4u) != -2) nInter += nact;
+                }
             }
-        }
-        qTop = max(qTop - 16u * kWalkBatch, qBase);
-        mTop = max(mTop - 8u * kWalkBatch, mBase);
-        __syncwarp();  // pushes of this batch before the next refill reads them
+            qTop = max(qTop - 16u * kWalkBatch, qBase);
+            mTop = max(mTop - 8u * kWalkBatch, mBase);
+            // go on while no active group is short of a batch with cells to pop (-> refill) or out of work (-> next group);
+            // a group that is merely running out (a few children left, nothing stacked) just takes dummies
+        } while (!__any_sync(kFull, active && qTop < qBase + 16u * kWalkBatch && (stkTop != stkBase || spilled != 0 || qTop == qBase)));
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -771,23 +854,11 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const float4 *__rest
             atomicAdd(&sc->opens, nOpen);
         }
     }
-    const size_t phase = (size_t)(sc->step & 1) * dst.phaseStride;
-    if (nact == 2) {
-        const float4 a0 = make_float4(ax.x, ay.x, az.x, 0.0f), a1 = make_float4(ax.y, ay.y, az.y, 0.0f);
-        for (int r = 0; r < dst.count; ++r) {  // own buffer, then the peers' (NVLink stores)
-            float4 *out = dst.buf[r] + phase + k0;
-            out[0] = a0;
-            out[1] = a1;
-        }
-    } else if (nact == 1) {
-        const float4 a0 = make_float4(ax.x, ay.x, az.x, 0.0f);
-        for (int r = 0; r < dst.count; ++r) dst.buf[r][phase + k0] = a0;
-    }
 }
 
 // ---- 5b. the deep walk: one shared stack per warp, 64 levels ---------------------------------------------------
-// Round 1's walk, kept as the fallback for trees too deep for walk_kernel's shared-memory stacks (sc->deep)
-// and for the non-reference 32-wide vote.  A stack entry is {cell - N, one bit per group that still needs the
+// Round 1's walk, kept for the non-reference 32-wide vote and as a second implementation to validate and time
+// walk_kernel against (bh_set_force_deep_walk).  A stack entry is {cell - N, one bit per group that still needs the
 // cell | depth << 1}; a group that accepted a cell is simply absent from the mask of its children; the warp
 // walks the union of its groups' trees.  Per pop one LDG.128 per lane brings the cell's walk record (8
 // children + 8 {threshold, entry} pairs) into a per-warp shared-memory row; the children are consumed with
@@ -797,7 +868,7 @@ constexpr int kStackCap = 7 * kMaxDepth + 8;  // a popped cell pushes at most 8 
 constexpr int kForce2Threads = 128;
 constexpr int kForce2Bodies = 2 * kForce2Threads;  // per CTA
 
-template <int VOTE, bool ONLY_IF_DEEP, bool COUNT>
+template <int VOTE, bool COUNT>
 __global__ void __launch_bounds__(kForce2Threads) deep_walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
                                                                     const int2 *__restrict__ ometa, const int *__restrict__ meta,
                                                                     const int *__restrict__ perm, const PeerBuffers dst, Scalars *sc,
@@ -806,7 +877,6 @@ __global__ void __launch_bounds__(kForce2Threads) deep_walk_kernel(const float4 
     __shared__ int2 stack[kForce2Threads / 32][kStackCap];  // {cell - N, group bits | depth << 1}
     __shared__ float4 stage[kForce2Threads / 32][12];       // the popped cell's walk record: 8 children, 8 {threshold, entry}
     if (sc->error != 0) return;
-    if (ONLY_IF_DEEP && sc->deep == 0) return;
     const int maxDepth = sc->maxDepth;
     if (maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;

@@ -37,6 +37,7 @@ struct Sim {
     unsigned long long *flags = nullptr, *seq = nullptr;
     int2 *ometa = nullptr;
     int *child = nullptr, *start = nullptr, *count = nullptr, *perm = nullptr, *meta = nullptr, *parent = nullptr, *arrived = nullptr;
+    int *spill = nullptr;  // the walk's stack spill area: kWalkSpillCap entries per group slot of every persistent CTA
     float *partials = nullptr;
     bh::Scalars *sc = nullptr;
     bh::Scalars *hostSc = nullptr;  // pinned mirror
@@ -47,7 +48,7 @@ struct Sim {
     bool havePerm = false;   // a sort has run since the upload
     bool permValid = false;  // perm[] refers to slots of the current buffers (false: bodies already lie in tree order)
     // launch geometry
-    int bboxGrid = 1, buildGrid = 1, summGrid = 1, sortGrid = 1, deepGrid = 1;
+    int bboxGrid = 1, buildGrid = 1, summGrid = 1, sortGrid = 1, walkGrid = 1;
     // options
     bool profiling = false, counting = false, forceDeep = false;
     int insertionOrder = 1;
@@ -143,23 +144,23 @@ void launchWalk(Sim *s, int first, int cnt, bool peers) {
     const bh::PeerBuffers dst = accDestinations(s, peers);
     const int *perm = s->permValid ? s->perm : nullptr;
     const float4 *body = s->body4[s->cur];
-    const int chunks = (cnt + bh::kForce2Bodies - 1) / bh::kForce2Bodies;
-    if (s->vote == 16) {
-        const int grid = (cnt + bh::kWalkBodies - 1) / bh::kWalkBodies;
-        const int deepGrid = std::min(chunks, s->deepGrid);
-        if (s->counting) {
-            bh::walk_kernel<true><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->n, first, cnt, s->eps, s->forceDeep);
-            bh::deep_walk_kernel<16, true, true><<<deepGrid, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
-        } else {
-            bh::walk_kernel<false><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->n, first, cnt, s->eps, s->forceDeep);
-            bh::deep_walk_kernel<16, true, false><<<deepGrid, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
-        }
-    } else {  // 32-wide votes (not reference-exact): the shared-stack walk only
+    if (s->vote == 16 && !s->forceDeep) {
+        // persistent CTAs; chunks of 2^shift vote groups are dealt round-robin to them
+        const int groups = (cnt + 15) / 16;
+        const int shift = groups >= s->walkGrid * 64 ? 5 : 3;
+        const int grid = std::max(1, std::min(s->walkGrid, (groups + (1 << shift) - 1) >> shift));
         if (s->counting)
-            bh::deep_walk_kernel<32, false, true><<<chunks, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+            bh::walk_kernel<true><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
         else
-            bh::deep_walk_kernel<32, false, false><<<chunks, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps);
+            bh::walk_kernel<false><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
+        return;
     }
+    // 32-wide votes (not reference-exact), or the shared-stack walk on request
+    const int chunks = (cnt + bh::kForce2Bodies - 1) / bh::kForce2Bodies;
+#define BH_DEEP(V, C) bh::deep_walk_kernel<V, C><<<chunks, bh::kForce2Threads, 0, s->stream>>>(body, s->octet, s->ometa, s->meta, perm, dst, s->sc, s->n, s->m, first, cnt, s->thetaMacro, s->eps)
+    if (s->vote == 16) { if (s->counting) BH_DEEP(16, true); else BH_DEEP(16, false); }
+    else { if (s->counting) BH_DEEP(32, true); else BH_DEEP(32, false); }
+#undef BH_DEEP
 }
 
 int launchBarrier(Sim *s) {
@@ -251,7 +252,7 @@ int launchStage(Sim *s, int stage, bool fused) {
         return fail(s, BH_ERR_ARG, "unknown stage %d", stage);
     }
     BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[stage] += (stage == BH_STAGE_FORCE && s->vote == 16) ? 2 : 1;
+    s->stageLaunches[stage] += 1;
     if (stage == BH_STAGE_FORCE && !fused) s->stageLaunches[stage]++;
     return BH_OK;
 }
@@ -346,7 +347,7 @@ int graphStep(Sim *s) {
     s->treePhase = parity;
     s->havePerm = true;
     if (willPermute) { s->cur = parity ^ 1; s->permValid = false; } else { s->permValid = true; }
-    for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st] += (st == BH_STAGE_FORCE && s->vote == 16) ? 2 : 1;
+    for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st] += 1;
     if (s->p2p) s->stageLaunches[BH_STAGE_FORCE]++;  // the peer barrier
     return BH_OK;
 }
@@ -490,7 +491,9 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     // tiny problems: do not launch more waiting threads than there can be cells
     const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
     s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
-    s->deepGrid = s->numSMs * 8;
+    s->walkGrid = s->numSMs * bh::kWalkCtasPerSM;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&s->spill), sizeof(int) * (size_t)s->walkGrid * bh::kWalkWarps * bh::kWalkGroups * bh::kWalkSpillCap)) != cudaSuccess)
+        return bail(BH_ERR_ALLOC, "cudaMalloc spill", e);
     for (int b = 0; b < 2; ++b) {
         if ((e = cudaMemsetAsync(s->body4[b], 0, sizeof(float4) * n, s->stream)) != cudaSuccess) return bail(BH_ERR_CUDA, "cudaMemset", e);
         cudaMemsetAsync(s->velacc[b], 0, sizeof(float4) * 2 * n, s->stream);
@@ -526,7 +529,7 @@ void bh_destroy(bh_sim *sim) {
     for (int b = 0; b < 2; ++b) { cudaFree(s->body4[b]); cudaFree(s->velacc[b]); }
     cudaFree(s->cell4); cudaFree(s->octet); cudaFree(s->ometa); cudaFree(s->accAlloc);
     cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->perm); cudaFree(s->meta); cudaFree(s->parent); cudaFree(s->arrived);
-    cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging);
+    cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging); cudaFree(s->spill);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
         for (auto &row : s->ev)
@@ -681,7 +684,7 @@ int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
     if (count == 0) return BH_OK;
     launchWalk(s, first, count, false);
     BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[BH_STAGE_FORCE] += s->vote == 16 ? 2 : 1;
+    s->stageLaunches[BH_STAGE_FORCE] += 1;
     return BH_OK;
 }
 
@@ -692,7 +695,7 @@ int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count) {
     if (count == 0) return BH_OK;
     launchWalk(s, first, count, true);
     BH_CUDA(s, cudaGetLastError());
-    s->stageLaunches[BH_STAGE_FORCE] += s->vote == 16 ? 2 : 1;
+    s->stageLaunches[BH_STAGE_FORCE] += 1;
     return BH_OK;
 }
 
@@ -901,7 +904,7 @@ int bh_stats(bh_sim *sim, bh_stats_t *out) {
     out->barrier_ms = s->stageMs[BH_STAGE_INTEGRATE];
     out->interactions = (int64_t)s->hostSc->interactions;
     out->opens = (int64_t)s->hostSc->opens;
-    out->deep_walk = s->hostSc->deep;
+    out->deep_walk = (s->vote != 16 || s->forceDeep) ? 1 : 0;
     return BH_OK;
 }
 
@@ -1013,6 +1016,19 @@ int bh_universe_file_bodies(const char *path, int32_t *nbodies) {
     UniverseFile u;
     if (!readUniverse(path, true, 0, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
     *nbodies = u.n;
+    return BH_OK;
+}
+
+int bh_read_universe_file(const char *path, int32_t capacity, float *x, float *y, float *z, float *vx, float *vy, float *vz, float *mass) {
+    float *dst[7] = {x, y, z, vx, vy, vz, mass};
+    if (!path) return fail(nullptr, BH_ERR_ARG, "path is NULL");
+    for (float *d : dst)
+        if (!d) return fail(nullptr, BH_ERR_ARG, "NULL output array");
+    UniverseFile u;
+    if (!readUniverse(path, true, 0, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
+    if (u.n > capacity) return fail(nullptr, BH_ERR_ARG, "%d bodies in the file, room for %d", u.n, capacity);
+    if (!readUniverse(path, false, 0, u)) return fail(nullptr, BH_ERR_ARG, "%s", u.error.c_str());
+    for (int a = 0; a < 7; ++a) memcpy(dst[a], u.arrays[a].data(), sizeof(float) * (size_t)u.n);
     return BH_OK;
 }
 

@@ -81,7 +81,7 @@ typedef struct bh_stats_t {
     int64_t interactions;     /* (body,node) force evaluations of the last counted force call */
     int64_t opens;            /* (body,cell) opening tests that pushed, same call */
     double barrier_ms;        /* summed CUDA-event time of the multi-GPU peer barrier (ABI >= 2) */
-    int32_t deep_walk;        /* 1 = the last force stage was redone by the deep-tree walk kernel (ABI >= 2) */
+    int32_t deep_walk;        /* 1 = the force stage runs the shared-stack walk kernel (vote width 32 or bh_set_force_deep_walk) */
     int32_t reserved;
 } bh_stats_t;
 
@@ -109,8 +109,8 @@ int bh_set_counting(bh_sim *sim, int32_t on);
  * that step's sorted (DFS / Morton-like) order, which is the next build's insertion order (coalesced
  * loads); 0 = bodies stay in upload order.  Results and everything bh_read returns are identical. */
 int bh_set_insertion_order(bh_sim *sim, int32_t mode);
-/* Debug/validation: 1 = always run the deep-tree fallback of the force walk (the kernel that takes over
- * when a tree is too deep for the fast walk's shared-memory stacks); 0 = automatic (default). */
+/* Validation / A-B timing: 1 = run the force stage with the shared-stack walk kernel (the one used for
+ * 32-wide votes) instead of the per-group walk; 0 = default.  Same results up to summation order. */
 int bh_set_force_deep_walk(bh_sim *sim, int32_t on);
 /* 1 (default) = bh_step replays one captured CUDA graph per step (six kernels, fixed arguments); 0 = six launches. */
 int bh_set_graph(bh_sim *sim, int32_t on);
@@ -208,6 +208,9 @@ int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out);
  * fails like the reference when the body count differs from the simulation's. */
 int bh_universe_file_bodies(const char *path, int32_t *nbodies);
 int bh_upload_universe_file(bh_sim *sim, const char *path);
+/* The loader alone (no device needed): fills caller-owned host arrays of `capacity` floats each. */
+int bh_read_universe_file(const char *path, int32_t capacity, float *x, float *y, float *z, float *vx, float *vy,
+                          float *vz, float *mass);
 /* UniverseSerializer.serialize (universe/serialize/UniverseSerializer.java:25-34) for the simulation's CURRENT
  * state, host numbering: a state dump every SerializedUniverseGenerator (Java or bh_upload_universe_file) reads. */
 int bh_write_universe_file(bh_sim *sim, const char *path);

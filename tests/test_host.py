@@ -113,3 +113,48 @@ def test_native_universe_reader_header(tmp_path):
     bad = tmp_path / "bad.universe"
     bad.write_bytes(b"\xac\xed\x00\x05\x73\x72" + b"\0" * 64)  # the legacy layout (writeObject(Integer) first)
     assert lib.bh_universe_file_bodies(str(bad).encode(), C.byref(n)) == -2
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "universes")), reason="the reference tree is only present in the build container")
+@pytest.mark.parametrize("name", ["sphericaluniverse1", "montecarlouniverse1"])
+def test_readers_on_the_reference_s_own_universe_files(name):
+    """universes/*.universe as shipped (UniverseSerializer.java:25-34): the Python reader and the native reader
+    (bh_read_universe_file, the loader behind bh_upload_universe_file) reproduce the committed fixtures bit for bit
+    (tests/golden/make_bundled_npz.py made them)."""
+    path = os.path.join(REFERENCE, "universes", name + ".universe")
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    n, arrs = U.read_universe(path)
+    lib = _lib.load()
+    cnt = C.c_int32()
+    assert lib.bh_universe_file_bodies(path.encode(), C.byref(cnt)) == 0 and cnt.value == n == 32768
+    nat = [np.full(n, np.nan, np.float32) for _ in range(7)]
+    assert lib.bh_read_universe_file(path.encode(), n, *(a.ctypes.data for a in nat)) == 0
+    assert lib.bh_read_universe_file(path.encode(), n - 1, *(a.ctypes.data for a in nat)) == -2  # no room
+    for got in (arrs, nat):
+        for k, a in zip("xyz", got[:3]):
+            assert np.array_equal(a.view(np.uint32), fix[k].view(np.uint32)), k
+        assert not got[3].any() and not got[4].any() and not got[5].any()
+        assert np.all(got[6] == fix["mass"][0])
+    # the legacy layout at the repository root (writeObject(Integer) first) is rejected, as by the current Java loader
+    legacy = os.path.join(REFERENCE, "sphericaluniverse1.universe")
+    if os.path.exists(legacy):
+        assert lib.bh_universe_file_bodies(legacy.encode(), C.byref(cnt)) == -2
+        with pytest.raises(ValueError):
+            U.read_universe(legacy)
+
+
+def test_native_reader_rejects_bad_headers(tmp_path):
+    """A negative or absurd body count in the header must come back as an error code, not as a C++ exception."""
+    lib = _lib.load()
+    n = C.c_int32()
+    for count in (-1, 0):
+        p = tmp_path / ("bad%d.universe" % count)
+        p.write_bytes(b"\xac\xed\x00\x05\x77\x04" + struct.pack(">i", count) + b"\x75" + b"\0" * 40)
+        assert lib.bh_universe_file_bodies(str(p).encode(), C.byref(n)) == -2
+    p = tmp_path / "huge.universe"
+    p.write_bytes(b"\xac\xed\x00\x05\x77\x04" + struct.pack(">i", 2 ** 31 - 1) + b"\x75" + b"\0" * 40)
+    buf = [np.zeros(4, np.float32) for _ in range(7)]
+    assert lib.bh_read_universe_file(str(p).encode(), 4, *(a.ctypes.data for a in buf)) == -2
