@@ -637,14 +637,23 @@ struct PeerBuffers {
 constexpr int kWalkThreads = 128;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kWalkGroups = 8;        // vote groups per warp (4 lanes x 4 bodies)
-constexpr int kWalkBatch = 6;         // children tested per group between two looks at the queue
-constexpr int kWalkQCap = 26;         // queued children per group
+#ifndef BH_WALK_BATCH  // (tuning knobs: scripts/walk_variants.sh builds and times alternatives)
+#define BH_WALK_BATCH 12
+#define BH_WALK_SUB 6
+#define BH_WALK_TRIPS 5
+#define BH_WALK_SCAP 64
+#define BH_WALK_CTAS 4
+#endif
+constexpr int kWalkBatch = BH_WALK_BATCH;  // children tested per group and pass
+constexpr int kWalkSub = BH_WALK_SUB;      // ... in sub-batches of this many, whose loads are issued up front
+constexpr int kWalkTrips = BH_WALK_TRIPS;  // cells a group pops per pass, at most
+constexpr int kWalkQCap = kWalkBatch + 8;  // queued children per group: a group pops while 8 slots (any cell) are free
 constexpr int kWalkSlots = kWalkBatch + kWalkQCap;  // the lowest kWalkBatch slots hold zero-mass dummies
-constexpr int kWalkSCap = 128;        // stacked cells per group in shared memory
-constexpr int kWalkSpill = 64;        // entries moved to / from the global spill buffer at a time
+constexpr int kWalkSCap = BH_WALK_SCAP;    // stacked cells per group in shared memory
+constexpr int kWalkSpill = 32;        // entries moved to / from the global spill buffer at a time
 constexpr int kWalkSpillCap = 1024;   // spill entries per group slot (7 * 64 + 8 would do)
-constexpr int kWalkRefillCells = 6;   // cells a group pops per refill, at most
-constexpr int kWalkCtasPerSM = 5;
+constexpr int kWalkCtasPerSM = BH_WALK_CTAS;
+static_assert(kWalkBatch % kWalkSub == 0 && kWalkSCap >= kWalkSpill + kWalkBatch + 8, "walk tuning");
 
 struct WalkShared {
     // +1 padding: the groups' arrays start 4 (2, 1) banks apart, so equal indices in different groups do not collide
@@ -659,7 +668,8 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                                                                             const int2 *__restrict__ ometa, const int *__restrict__ perm,
                                                                             const PeerBuffers dst, Scalars *sc, int *__restrict__ spill, int n,
                                                                             int first, int cnt, float eps, int chunkShift) {
-    __shared__ WalkShared sh;
+    extern __shared__ float4 walkSharedRaw[];  // dynamic: more than the 48 KB a static array may have
+    WalkShared &sh = *reinterpret_cast<WalkShared *>(walkSharedRaw);
     if (sc->error != 0) return;
     if (sc->maxDepth > kMaxDepth) {  // calculateforce.cl:69-73
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->error = 1;
@@ -747,27 +757,25 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
             }
             if (__all_sync(kFull, !active)) break;
         }
-        // ---- refill: when any group is short of a batch, every group tops its queue up --------------------------
-        if (__any_sync(kFull, qTop < qBase + 16u * kWalkBatch && (stkTop != stkBase || spilled != 0))) {
-            if (__any_sync(kFull, stkTop == stkBase && spilled != 0)) {  // (cold) a dry stack takes spilled entries back
-                if (stkTop == stkBase && spilled != 0) {
-                    const int take = min(spilled, kWalkSpill);
-                    spilled -= take;
-                    for (int t = l; t < take; t += 4) sts_s32(stkBase + 4u * (unsigned)t, mySpill[spilled + t]);
-                    stkTop = stkBase + 4u * (unsigned)take;
-                }
-                __syncwarp();
+        // ---- refill: every pass, every group pops up to kWalkTrips cells while its queue has room for any cell ------
+        // (a group's schedule depends on its own state only: its result is bit-reproducible whichever slot, warp or
+        // launch configuration -- whole universe or one rank's slice -- it runs in)
+        if (__any_sync(kFull, stkTop == stkBase && spilled != 0)) {  // (cold) a dry stack takes spilled entries back
+            if (stkTop == stkBase && spilled != 0) {
+                const int take = min(spilled, kWalkSpill);
+                spilled -= take;
+                for (int t = l; t < take; t += 4) sts_s32(stkBase + 4u * (unsigned)t, mySpill[spilled + t]);
+                stkTop = stkBase + 4u * (unsigned)take;
             }
+            __syncwarp();
+        }
+        {
             int room = kWalkQCap - ((int)(qTop - qBase) >> 4);
-            bool alive = active;
 #pragma unroll
-            for (int r = 0; r < kWalkRefillCells; ++r) {
-                alive = alive && stkTop != stkBase;
-                int e = 0;
-                if (alive) e = lds_s32(stkTop - 4u);
-                const int c = ((e >> 27) & 7) + 1;  // children of the cell on top of the stack
-                alive = alive && c <= room;
-                if (alive) {
+            for (int r = 0; r < kWalkTrips; ++r) {
+                if (active && stkTop != stkBase && room >= 8) {
+                    const int e = lds_s32(stkTop - 4u);
+                    const int c = ((e >> 27) & 7) + 1;  // children of the cell on top of the stack
                     const int rel = e & kEntryMask;
                     const float4 *src = octet + (size_t)rel * 8 + l;
                     const int2 *msrc = ometa + (size_t)rel * 8 + l;
@@ -783,35 +791,43 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
             cp_async_wait_all();
             __syncwarp();
         }
-        // ---- batches, back to back until some group must refill or has finished ---------------------------------
-        do {
-            if (__any_sync(kFull, stkTop > stkLimit)) {  // (cold) no room for the pushes of another batch: spill the bottom entries
-                if (stkTop > stkLimit) {
-                    if (spilled + kWalkSpill > kWalkSpillCap) {
-                        atomicCAS(&sc->error, 0, 2);  // cannot happen for trees of at most 64 levels
-                    } else {
-                        const int rest = ((int)(stkTop - stkBase) >> 2) - kWalkSpill;  // 58..64 entries stay
-                        int keep[kWalkSpill / 4];
+        if (__any_sync(kFull, stkTop > stkLimit)) {  // (cold) no room for the pushes of another batch: spill the bottom entries
+            if (stkTop > stkLimit) {
+                if (spilled + kWalkSpill > kWalkSpillCap) {
+                    atomicCAS(&sc->error, 0, 2);  // cannot happen for trees of at most 64 levels
+                } else {
+                    const int rest = ((int)(stkTop - stkBase) >> 2) - kWalkSpill;  // entries that stay
+                    int keep[kWalkSpill / 4];
 #pragma unroll
-                        for (int t = 0; t < kWalkSpill / 4; ++t) {
-                            mySpill[spilled + l + 4 * t] = lds_s32(stkBase + 4u * (unsigned)(l + 4 * t));
-                            keep[t] = (l + 4 * t < rest) ? lds_s32(stkBase + 4u * (unsigned)(kWalkSpill + l + 4 * t)) : 0;
-                        }
-                        __syncwarp(gm);
-#pragma unroll
-                        for (int t = 0; t < kWalkSpill / 4; ++t)
-                            if (l + 4 * t < rest) sts_s32(stkBase + 4u * (unsigned)(l + 4 * t), keep[t]);
-                        spilled += kWalkSpill;
-                        stkTop -= 4u * kWalkSpill;
+                    for (int t = 0; t < kWalkSpill / 4; ++t) {
+                        mySpill[spilled + l + 4 * t] = lds_s32(stkBase + 4u * (unsigned)(l + 4 * t));
+                        keep[t] = (l + 4 * t < rest) ? lds_s32(stkBase + 4u * (unsigned)(kWalkSpill + l + 4 * t)) : 0;
                     }
-                }
-                __syncwarp();
-            }
-            // ---- one batch: the top kWalkBatch queued children of every group (dummies below a short queue) ----------
+                    __syncwarp(gm);
 #pragma unroll
-            for (int i = 1; i <= kWalkBatch; ++i) {
-                const float4 c = lds_v4(qTop - 16u * i);
-                const float thr = lds_f32(mTop - 8u * i);
+                    for (int t = 0; t < kWalkSpill / 4; ++t)
+                        if (l + 4 * t < rest) sts_s32(stkBase + 4u * (unsigned)(l + 4 * t), keep[t]);
+                    spilled += kWalkSpill;
+                    stkTop -= 4u * kWalkSpill;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- one batch: the top kWalkBatch queued children of every group (dummies below a short queue) ------------
+#pragma unroll
+        for (int h = 0; h < kWalkBatch; h += kWalkSub) {
+            float4 cs[kWalkSub];
+            float thrs[kWalkSub];
+#pragma unroll
+            for (int i = 0; i < kWalkSub; ++i) {  // the loads of a sub-batch first: their latency overlaps the first children's math
+                cs[i] = lds_v4(qTop - 16u * (unsigned)(h + i + 1));
+                thrs[i] = lds_f32(mTop - 8u * (unsigned)(h + i + 1));
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkSub; ++i) {
+                const float4 c = cs[i];
+                const float thr = thrs[i];
+                const unsigned entAddr = mTop - 8u * (unsigned)(h + i + 1) + 4u;
                 const float2 cx2 = make_float2(c.x, c.x), cy2 = make_float2(c.y, c.y), cz2 = make_float2(c.z, c.z);
                 const float2 dxA = __fadd2_rn(cx2, npxA), dyA = __fadd2_rn(cy2, npyA), dzA = __fadd2_rn(cz2, npzA);  // c - p, exactly
                 const float2 dxB = __fadd2_rn(cx2, npxB), dyB = __fadd2_rn(cy2, npyB), dzB = __fadd2_rn(cz2, npzB);
@@ -830,19 +846,17 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                 axA = __ffma2_rn(dxA, fA, axA); ayA = __ffma2_rn(dyA, fA, ayA); azA = __ffma2_rn(dzA, fA, azA);  // :149-151
                 axB = __ffma2_rn(dxB, fB, axB); ayB = __ffma2_rn(dyB, fB, ayB); azB = __ffma2_rn(dzB, fB, azB);
                 if (open) {  // all lanes of the group store the same entry to the same address
-                    sts_s32(stkTop, lds_s32(mTop - 8u * i + 4u));
+                    sts_s32(stkTop, lds_s32(entAddr));
                     stkTop += 4;
                 }
                 if (COUNT) {
                     if (open) nOpen += nact;
-                    else if (lds_s32(mTop - 8u * i + 4u) != -2) nInter += nact;
+                    else if (lds_s32(entAddr) != -2) nInter += nact;
                 }
             }
-            qTop = max(qTop - 16u * kWalkBatch, qBase);
-            mTop = max(mTop - 8u * kWalkBatch, mBase);
-            // go on while no active group is short of a batch with cells to pop (-> refill) or out of work (-> next group);
-            // a group that is merely running out (a few children left, nothing stacked) just takes dummies
-        } while (!__any_sync(kFull, active && qTop < qBase + 16u * kWalkBatch && (stkTop != stkBase || spilled != 0 || qTop == qBase)));
+        }
+        qTop = max(qTop - 16u * kWalkBatch, qBase);
+        mTop = max(mTop - 8u * kWalkBatch, mBase);
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {

@@ -149,10 +149,11 @@ void launchWalk(Sim *s, int first, int cnt, bool peers) {
         const int groups = (cnt + 15) / 16;
         const int shift = groups >= s->walkGrid * 64 ? 5 : 3;
         const int grid = std::max(1, std::min(s->walkGrid, (groups + (1 << shift) - 1) >> shift));
+        const size_t smem = sizeof(bh::WalkShared);
         if (s->counting)
-            bh::walk_kernel<true><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
+            bh::walk_kernel<true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
         else
-            bh::walk_kernel<false><<<grid, bh::kWalkThreads, 0, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
+            bh::walk_kernel<false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
         return;
     }
     // 32-wide votes (not reference-exact), or the shared-stack walk on request
@@ -491,7 +492,11 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     // tiny problems: do not launch more waiting threads than there can be cells
     const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
     s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
-    s->walkGrid = s->numSMs * bh::kWalkCtasPerSM;
+    cudaFuncSetAttribute(bh::walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
+    cudaFuncSetAttribute(bh::walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
+    perSM = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::walk_kernel<false>, bh::kWalkThreads, sizeof(bh::WalkShared));
+    s->walkGrid = s->numSMs * std::max(1, std::min(perSM, bh::kWalkCtasPerSM));
     if ((e = cudaMalloc(reinterpret_cast<void **>(&s->spill), sizeof(int) * (size_t)s->walkGrid * bh::kWalkWarps * bh::kWalkGroups * bh::kWalkSpillCap)) != cudaSuccess)
         return bail(BH_ERR_ALLOC, "cudaMalloc spill", e);
     for (int b = 0; b < 2; ++b) {
