@@ -622,26 +622,28 @@ struct PeerBuffers {
 // -- eight different children, each against its own group's 16 bodies (LDS.128 with one address per group) --
 // so no lane ever works on a node its group does not need (a shared walk of the groups' union costs ~25 % more
 // child tests), and the per-cell bookkeeping of a stack walk (pop, row fetch, loop control: a third of the
-// issue slots of a pop-per-cell design) is paid once per ~20 children: when any group's queue runs low, every
-// group tops its queue up, popping cells from its stack and copying their walk records -- children {x,y,z,m}
-// and {threshold, entry}, one 128-byte and one 64-byte line per cell -- with LDGSTS straight into the queue.
-// Per child (128 interactions): LDS.128 + LDS.32, 14 packed fp32 (distances), 3 FMNMX + FSETP + VOTE + LOP3
-// (the group's vote, :145), 4 MUFU.RSQ, 12 packed fp32 (the interactions; zero mass if the group opens the
-// cell), predicated push: 26 of ~42 issue slots are packed fp32, so the kernel is bound by the fp32 pipe,
-// not by issue.  CTAs are persistent: a group slot whose walk is finished writes its accelerations and takes
-// the next group of the CTA's current chunk (chunks of 2^chunkShift groups are dealt round-robin to the CTAs), so a warp
+// issue slots of a pop-per-cell design) is paid once per pass of kWalkBatch children: at the top of a pass
+// every group pops up to kWalkTrips cells from its stack -- while its queue has room for any cell -- and
+// LDGSTS copies their walk records (children {x,y,z,m} and {threshold, entry}: one 128-byte and one 64-byte
+// line per cell) straight into the queue.  What a group does depends on its own state only, so its result is
+// bit-identical in whatever slot, warp, grid or slice it is computed (single-GPU run == any rank's run).
+// Per child (128 interactions): LDS.128 + LDS.32, 14 packed fp32 (distances), FMNMX + FMNMX3 + FSETP + VOTE +
+// LOP3 (the group's vote, :145), 4 MUFU.RSQ, 12 packed fp32 (the interactions; zero mass if the group opens
+// the cell; the mass is multiplied in last so that the vote is off the critical path), predicated push.
+// CTAs are persistent: a group slot whose walk is finished writes its accelerations and takes the next group
+// of the CTA's current chunk (chunks of 2^chunkShift groups are dealt round-robin to the CTAs), so a warp
 // never waits for its slowest group.
-// A group's cell stack holds 128 entries in shared memory; in deep trees (7 open siblings per level) its bottom
-// half is spilled to a per-slot global buffer and comes back when the shared part runs dry, so any tree the
-// reference accepts (64 levels) is walked by this kernel.
+// A group's cell stack holds kWalkSCap entries in shared memory; in deep trees (7 open siblings per level)
+// its bottom entries are spilled to a per-slot global buffer and come back when the shared part runs dry, so
+// any tree the reference accepts (64 levels) is walked by this kernel.
 constexpr int kWalkThreads = 128;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kWalkGroups = 8;        // vote groups per warp (4 lanes x 4 bodies)
 #ifndef BH_WALK_BATCH  // (tuning knobs: scripts/walk_variants.sh builds and times alternatives)
-#define BH_WALK_BATCH 12
-#define BH_WALK_SUB 6
-#define BH_WALK_TRIPS 5
-#define BH_WALK_SCAP 64
+#define BH_WALK_BATCH 16
+#define BH_WALK_SUB 8
+#define BH_WALK_TRIPS 6
+#define BH_WALK_SCAP 96
 #define BH_WALK_CTAS 4
 #endif
 constexpr int kWalkBatch = BH_WALK_BATCH;  // children tested per group and pass
@@ -650,7 +652,7 @@ constexpr int kWalkTrips = BH_WALK_TRIPS;  // cells a group pops per pass, at mo
 constexpr int kWalkQCap = kWalkBatch + 8;  // queued children per group: a group pops while 8 slots (any cell) are free
 constexpr int kWalkSlots = kWalkBatch + kWalkQCap;  // the lowest kWalkBatch slots hold zero-mass dummies
 constexpr int kWalkSCap = BH_WALK_SCAP;    // stacked cells per group in shared memory
-constexpr int kWalkSpill = 32;        // entries moved to / from the global spill buffer at a time
+constexpr int kWalkSpill = 64;        // entries moved to / from the global spill buffer at a time
 constexpr int kWalkSpillCap = 1024;   // spill entries per group slot (7 * 64 + 8 would do)
 constexpr int kWalkCtasPerSM = BH_WALK_CTAS;
 static_assert(kWalkBatch % kWalkSub == 0 && kWalkSCap >= kWalkSpill + kWalkBatch + 8, "walk tuning");
