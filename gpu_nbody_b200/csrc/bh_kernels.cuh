@@ -58,7 +58,7 @@ struct Scalars {
     int maxDepth;     // init 1, running max (buildtree.cl:199)
     int bottom;
     int error;
-    int deep;         // (unused since the walk spills its stacks)
+    int walkTicket;   // next chunk of eight vote groups the force walk hands to a warp (reset before every walk)
     int rootEntry;    // walk entry of the root cell (written by summarise)
     unsigned long long interactions;
     unsigned long long opens;
@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(const float4 *__rest
         start[m - n] = 0;
         count[m - n] = -1;
         arrived[m - n] = 0;  // level 0, no child cells yet, no reports
-        sc->deep = 0;
         sc->step = sc->step + 1;
     }
 }
@@ -630,9 +629,9 @@ struct PeerBuffers {
 // Per child (128 interactions): LDS.128 + LDS.32, 14 packed fp32 (distances), FMNMX + FMNMX3 + FSETP + VOTE +
 // LOP3 (the group's vote, :145), 4 MUFU.RSQ, 12 packed fp32 (the interactions; zero mass if the group opens
 // the cell; the mass is multiplied in last so that the vote is off the critical path), predicated push.
-// CTAs are persistent: a group slot whose walk is finished writes its accelerations and takes the next group
-// of the CTA's current chunk (chunks of 2^chunkShift groups are dealt round-robin to the CTAs), so a warp
-// never waits for its slowest group.
+// CTAs are persistent: a group slot whose walk is finished writes its accelerations and takes the next group of
+// its warp's chunk (eight consecutive groups, drawn from a global ticket), so a warp never waits for its slowest
+// group and all warps of the grid finish within one group walk of each other.
 // A group's cell stack holds kWalkSCap entries in shared memory; in deep trees (7 open siblings per level)
 // its bottom entries are spilled to a per-slot global buffer and come back when the shared part runs dry, so
 // any tree the reference accepts (64 levels) is walked by this kernel.
@@ -662,14 +661,13 @@ struct WalkShared {
     int stk[kWalkWarps][kWalkGroups][kWalkSCap + 1];
     float4 rec[kWalkWarps][kWalkGroups][kWalkSlots + 1];
     int2 meta[kWalkWarps][kWalkGroups][kWalkSlots + 1];
-    int next;  // next group of the CTA's schedule
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
                                                                             const int2 *__restrict__ ometa, const int *__restrict__ perm,
                                                                             const PeerBuffers dst, Scalars *sc, int *__restrict__ spill, int n,
-                                                                            int first, int cnt, float eps, int chunkShift) {
+                                                                            int first, int cnt, float eps) {
     extern __shared__ float4 walkSharedRaw[];  // dynamic: more than the 48 KB a static array may have
     WalkShared &sh = *reinterpret_cast<WalkShared *>(walkSharedRaw);
     if (sc->error != 0) return;
@@ -680,7 +678,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, l = lane & 3;
-    if (threadIdx.x == 0) sh.next = kWalkWarps * kWalkGroups;
     if (l == 0) {
 #pragma unroll
         for (int i = 0; i < kWalkBatch; ++i) {  // dummies: zero mass, always accepted, never counted
@@ -701,14 +698,14 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
     const unsigned stkLimit = stkBase + 4u * (kWalkSCap - kWalkBatch);  // a batch pushes at most kWalkBatch cells
     const unsigned qBase = (unsigned)__cvta_generic_to_shared(&sh.rec[warp][g][kWalkBatch]);
     const unsigned mBase = (unsigned)__cvta_generic_to_shared(&sh.meta[warp][g][kWalkBatch]);
-    const unsigned nextAddr = (unsigned)__cvta_generic_to_shared(&sh.next);
     unsigned stkTop = stkBase, qTop = qBase, mTop = mBase;  // one past the top entry; the same in all lanes of a group
     int *const mySpill = spill + ((size_t)(blockIdx.x * kWalkWarps + warp) * kWalkGroups + g) * kWalkSpillCap;
     int spilled = 0;  // entries of my group's stack that live in the spill buffer (below the shared-memory part)
-    // the group this slot works on
-    int idx = warp * kWalkGroups + g;  // position in the CTA's schedule
+    // the group this slot works on; the warp draws chunks of eight consecutive groups from a global ticket, so that
+    // all warps of the grid finish within one group walk of each other whatever the groups cost
     bool active = false;               // the slot has a group
-    bool fetch = true;                 // the slot wants the group at `idx`
+    bool fetch = true;                 // the slot wants its first group
+    int chunkNext = 0, chunkEnd = 0;   // unassigned groups of the warp's current chunk (the same in all lanes)
     int k0 = 0, nact = 0;
     float2 npxA = make_float2(0.f, 0.f), npyA = npxA, npzA = npxA, npxB = npxA, npyB = npxA, npzB = npxA;
     float2 axA = npxA, ayA = npxA, azA = npxA, axB = npxA, ayB = npxA, azB = npxA;
@@ -726,17 +723,23 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                     for (int t = 0; t < 4; ++t)
                         if (t < nact) out[t] = a[t];
                 }
-                int nx = 0;
-                if (l == 0) asm volatile("atom.shared.add.s32 %0, [%1], 1;" : "=r"(nx) : "r"(nextAddr) : "memory");
-                idx = __shfl_sync(gm, nx, lane & ~3);
             }
-            if (finished || fetch) {
+            const bool want = finished || fetch;
+            const unsigned wantMask = __ballot_sync(kFull, want && l == 0);  // one bit per slot that wants a group
+            const int need = __popc(wantMask), have = chunkEnd - chunkNext;
+            int fresh = 0;
+            if (need > have) {  // the rest of the current chunk does not cover them: draw the next chunk
+                if (lane == 0) fresh = atomicAdd(&sc->walkTicket, 1) * kWalkGroups;
+                fresh = __shfl_sync(kFull, fresh, 0);
+            }
+            if (want) {
                 fetch = false;
-                // chunks of 2^chunkShift consecutive groups are dealt round-robin to the CTAs
-                const long long grp = (((long long)blockIdx.x + (long long)(idx >> chunkShift) * gridDim.x) << chunkShift) + (idx & ((1 << chunkShift) - 1));
+                const int r = __popc(wantMask & ((1u << (lane & ~3)) - 1u));  // my rank among the slots that want one
+                const int grp = r < have ? chunkNext + r : fresh + (r - have);
                 active = grp < totalGroups;
+                nact = 0;
                 if (active) {
-                    const int gfirst = first + (int)grp * 16;  // the group's first sorted slot (exists)
+                    const int gfirst = first + grp * 16;  // the group's first sorted slot (exists)
                     k0 = gfirst + 4 * l;
                     nact = min(4, max(0, end - k0));
                     // a slot past the end borrows the position of the group's first body: its vote then equals that body's
@@ -753,10 +756,9 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                     stkTop = stkBase + 4;
                     qTop = qBase;
                     mTop = mBase;
-                } else {
-                    nact = 0;
                 }
             }
+            if (need > have) { chunkNext = fresh + (need - have); chunkEnd = fresh + kWalkGroups; } else { chunkNext += need; }
             if (__all_sync(kFull, !active)) break;
         }
         // ---- refill: every pass, every group pops up to kWalkTrips cells while its queue has room for any cell ------

@@ -145,15 +145,15 @@ void launchWalk(Sim *s, int first, int cnt, bool peers) {
     const int *perm = s->permValid ? s->perm : nullptr;
     const float4 *body = s->body4[s->cur];
     if (s->vote == 16 && !s->forceDeep) {
-        // persistent CTAs; chunks of 2^shift vote groups are dealt round-robin to them
+        // persistent CTAs; their warps draw chunks of eight vote groups from a ticket in the scalars
         const int groups = (cnt + 15) / 16;
-        const int shift = groups >= s->walkGrid * 64 ? 5 : 3;
-        const int grid = std::max(1, std::min(s->walkGrid, (groups + (1 << shift) - 1) >> shift));
+        const int grid = std::max(1, std::min(s->walkGrid, (groups + 31) / 32));
         const size_t smem = sizeof(bh::WalkShared);
+        cudaMemsetAsync(&s->sc->walkTicket, 0, sizeof(int), s->stream);
         if (s->counting)
-            bh::walk_kernel<true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
+            bh::walk_kernel<true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         else
-            bh::walk_kernel<false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps, shift);
+            bh::walk_kernel<false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         return;
     }
     // 32-wide votes (not reference-exact), or the shared-stack walk on request
