@@ -641,7 +641,7 @@ constexpr int kWalkGroups = 8;        // vote groups per warp (4 lanes x 4 bodie
 #ifndef BH_WALK_BATCH  // (tuning knobs: scripts/walk_variants.sh builds and times alternatives)
 #define BH_WALK_BATCH 16
 #define BH_WALK_SUB 8
-#define BH_WALK_TRIPS 6
+#define BH_WALK_TRIPS 5
 #define BH_WALK_SCAP 96
 #define BH_WALK_CTAS 4
 #endif

@@ -10,10 +10,10 @@ build() {  # name batch sub trips scap ctas
        -DBH_WALK_BATCH=$2 -DBH_WALK_SUB=$3 -DBH_WALK_TRIPS=$4 -DBH_WALK_SCAP=$5 -DBH_WALK_CTAS=$6 -Xptxas -v \
        -o gpu_nbody_b200/variants/$1.so gpu_nbody_b200/csrc/bhstep.cu 2>&1 | grep -A2 "walk_kernelILb0" | grep Used | sed "s/^/$1: /"
 }
-build b16s8t6c4 16 8 6 64 4 &
-build b24s8t9c3 24 8 9 64 3 &
-build b24s6t9c3 24 6 9 64 3 &
-build b32s8t12c3 32 8 12 80 3 &
-build b20s10t8c4 20 10 8 64 4 &
-build b24s8t9c4 24 8 9 64 4 &
+build b16s8t6c4 16 8 6 96 4 &
+build b16s8t6c5 16 8 6 96 5 &
+build b12s6t5c5 12 6 5 96 5 &
+build b20s10t8c4 20 10 8 96 4 &
+build b16s8t5c4 16 8 5 96 4 &
+build b16s8t7c4 16 8 7 96 4 &
 wait
