@@ -36,6 +36,9 @@ public final class BhStep implements AutoCloseable {
 	private static final MethodHandle READ = fn("bh_read", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
 	private static final MethodHandle COPY_VERTICES = fn("bh_copy_vertices", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 	private static final MethodHandle NUMBER_OF_NODES = fn("bh_number_of_nodes", FunctionDescriptor.of(JAVA_INT, JAVA_INT));
+	private static final MethodHandle SET_THETA_MACRO = fn("bh_set_theta_macro", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_FLOAT));
+	private static final MethodHandle SET_VERTEX_BUFFERS = fn("bh_set_vertex_buffers", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+	private static final MethodHandle WRITE_UNIVERSE = fn("bh_write_universe_file", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
 	private static final String[] STAGES = { "bh_bounding_box", "bh_build_tree", "bh_summarize", "bh_sort", "bh_calculate_force", "bh_integrate" };
 	private static final MethodHandle[] STAGE = new MethodHandle[STAGES.length];
 	static {
@@ -79,6 +82,9 @@ public final class BhStep implements AutoCloseable {
 	public void upload(final float[] x, final float[] y, final float[] z, final float[] vx, final float[] vy, final float[] vz, final float[] mass) {
 		try (Arena a = Arena.ofConfined()) {
 			final float[][] src = { x, y, z, vx, vy, vz, mass };
+			for (final float[] arr : src)
+				if (arr == null || arr.length < nbodies)
+					throw new IllegalArgumentException("universe arrays must hold at least nbodies elements");
 			final MemorySegment[] seg = new MemorySegment[7];
 			for (int i = 0; i < 7; ++i) {
 				seg[i] = a.allocate(JAVA_FLOAT, nbodies);
@@ -116,6 +122,8 @@ public final class BhStep implements AutoCloseable {
 
 	/** Replaces commandQueue.readBuffer(mem) + mem.getData() (GPUBH:277-278,294-295,306-312). */
 	public float[] readFloats(final int which, final int count) {
+		if (count < 0)
+			throw new IllegalArgumentException("count < 0");
 		try (Arena a = Arena.ofConfined()) {
 			final MemorySegment dst = a.allocate(JAVA_FLOAT, count);
 			check((int) READ.invokeExact(sim, which, dst, (long) count));
@@ -128,6 +136,8 @@ public final class BhStep implements AutoCloseable {
 	}
 
 	public int[] readInts(final int which, final int count) {
+		if (count < 0)
+			throw new IllegalArgumentException("count < 0");
 		try (Arena a = Arena.ofConfined()) {
 			final MemorySegment dst = a.allocate(JAVA_INT, count);
 			check((int) READ.invokeExact(sim, which, dst, (long) count));
@@ -137,6 +147,46 @@ public final class BhStep implements AutoCloseable {
 		} catch (final Throwable t) {
 			throw new IllegalStateException(t);
 		}
+	}
+
+	/** The THETA macro of calculateforce.cl:15-16 (= theta^2), e.g. the shipped 1.5f. */
+	public void setThetaMacro(final float thetaMacro) {
+		try {
+			check((int) SET_THETA_MACRO.invokeExact(sim, thetaMacro));
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** GL_INTEROP without host staging: DEVICE addresses of two float4[nbodies] buffers (CUDA-mapped GL vertex buffers). */
+	public void setVertexBuffers(final long pos4Device, final long vel4Device) {
+		try {
+			check((int) SET_VERTEX_BUFFERS.invokeExact(sim, MemorySegment.ofAddress(pos4Device), MemorySegment.ofAddress(vel4Device)));
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** UniverseSerializer.serialize of the current device state (UniverseSerializer.java:25-34). */
+	public void writeUniverseFile(final String path) {
+		try (Arena a = Arena.ofConfined()) {
+			check((int) WRITE_UNIVERSE.invokeExact(sim, a.allocateFrom(path)));
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** Replaces the copyVertices kernel launch (GPUBH:265-266) for direct NIO buffers of nbodies*4 floats each (either may be null). */
+	public void copyVertices(final java.nio.ByteBuffer pos4, final java.nio.ByteBuffer vel4) {
+		if ((pos4 != null && (!pos4.isDirect() || pos4.capacity() < 16L * nbodies)) || (vel4 != null && (!vel4.isDirect() || vel4.capacity() < 16L * nbodies)))
+			throw new IllegalArgumentException("copyVertices needs direct buffers of nbodies * 16 bytes");
+		copyVertices(pos4 == null ? MemorySegment.NULL : MemorySegment.ofBuffer(pos4), vel4 == null ? MemorySegment.NULL : MemorySegment.ofBuffer(vel4));
 	}
 
 	/** Replaces the copyVertices kernel launch (GPUBH:265-266); pos4/vel4 are nbodies*4 floats (mapped GL buffers or heap). */

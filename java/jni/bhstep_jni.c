@@ -5,8 +5,10 @@
  * installed:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I include java/jni/bhstep_jni.c \
  *       -L gpu_nbody_b200 -lbhstep -o libbhstep_jni.so
- * Java arrays are pinned with GetPrimitiveArrayCritical for the duration of the copy only (bh_upload / bh_read copy).
+ * Array lengths are validated before anything is touched; the data crosses through Get/SetXxxArrayRegion into malloc'd
+ * staging, so no JNI critical region is ever held across a CUDA call (cudaMalloc, pageable copies, stream syncs).
  */
+#include <stdlib.h>
 #include <jni.h>
 #include <stdint.h>
 
@@ -33,12 +35,19 @@ JNIEXPORT jint JNICALL J(numberOfNodes)(JNIEnv *env, jclass c, jint nbodies) { (
 JNIEXPORT jint JNICALL J(upload)(JNIEnv *env, jclass c, jlong sim, jfloatArray x, jfloatArray y, jfloatArray z, jfloatArray vx,
                                  jfloatArray vy, jfloatArray vz, jfloatArray mass) {
     jfloatArray arr[7] = {x, y, z, vx, vy, vz, mass};
-    float *p[7];
+    const int n = bh_number_of_bodies((bh_sim *)(intptr_t)sim);
+    float *stage;
     int i, rc;
     (void)c;
-    for (i = 0; i < 7; ++i) p[i] = (float *)(*env)->GetPrimitiveArrayCritical(env, arr[i], NULL);
-    rc = bh_upload((bh_sim *)(intptr_t)sim, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
-    for (i = 6; i >= 0; --i) (*env)->ReleasePrimitiveArrayCritical(env, arr[i], p[i], JNI_ABORT);
+    if (n <= 0) return BH_ERR_ARG;
+    for (i = 0; i < 7; ++i)
+        if (!arr[i] || (*env)->GetArrayLength(env, arr[i]) < n) return BH_ERR_ARG;
+    stage = (float *)malloc(sizeof(float) * 7 * (size_t)n);
+    if (!stage) return BH_ERR_ALLOC;
+    for (i = 0; i < 7; ++i) (*env)->GetFloatArrayRegion(env, arr[i], 0, n, stage + (size_t)i * n);
+    rc = bh_upload((bh_sim *)(intptr_t)sim, stage, stage + (size_t)n, stage + 2 * (size_t)n, stage + 3 * (size_t)n, stage + 4 * (size_t)n,
+                   stage + 5 * (size_t)n, stage + 6 * (size_t)n);
+    free(stage);
     return rc;
 }
 
@@ -62,24 +71,40 @@ JNIEXPORT jint JNICALL J(stage)(JNIEnv *env, jclass c, jlong sim, jint stage) {
 
 /* readBuffer + getData, GPUBH:277-278,294-295,306-312 */
 JNIEXPORT jint JNICALL J(readFloats)(JNIEnv *env, jclass c, jlong sim, jint which, jfloatArray dst, jint count) {
-    float *p = (float *)(*env)->GetPrimitiveArrayCritical(env, dst, NULL);
-    int rc = bh_read((bh_sim *)(intptr_t)sim, which, p, count);
+    float *stage;
+    int rc;
     (void)c;
-    (*env)->ReleasePrimitiveArrayCritical(env, dst, p, 0);
+    if (!dst || count < 0 || count > (*env)->GetArrayLength(env, dst)) return BH_ERR_ARG;
+    if (count == 0) return 0;
+    stage = (float *)malloc(sizeof(float) * (size_t)count);
+    if (!stage) return BH_ERR_ALLOC;
+    rc = bh_read((bh_sim *)(intptr_t)sim, which, stage, count);
+    if (rc == 0) (*env)->SetFloatArrayRegion(env, dst, 0, count, stage);
+    free(stage);
     return rc;
 }
 
 JNIEXPORT jint JNICALL J(readInts)(JNIEnv *env, jclass c, jlong sim, jint which, jintArray dst, jint count) {
-    jint *p = (jint *)(*env)->GetPrimitiveArrayCritical(env, dst, NULL);
-    int rc = bh_read((bh_sim *)(intptr_t)sim, which, p, count);
+    jint *stage;
+    int rc;
     (void)c;
-    (*env)->ReleasePrimitiveArrayCritical(env, dst, p, 0);
+    if (!dst || count < 0 || count > (*env)->GetArrayLength(env, dst)) return BH_ERR_ARG;
+    if (count == 0) return 0;
+    stage = (jint *)malloc(sizeof(jint) * (size_t)count);
+    if (!stage) return BH_ERR_ALLOC;
+    rc = bh_read((bh_sim *)(intptr_t)sim, which, stage, count);
+    if (rc == 0) (*env)->SetIntArrayRegion(env, dst, 0, count, stage);
+    free(stage);
     return rc;
 }
 
 /* copyVertices into direct ByteBuffers (e.g. mapped GL buffers), GPUBH:265-266 */
 JNIEXPORT jint JNICALL J(copyVertices)(JNIEnv *env, jclass c, jlong sim, jobject pos4, jobject vel4) {
+    const jlong need = 16 * (jlong)bh_number_of_bodies((bh_sim *)(intptr_t)sim);
     (void)c;
+    if ((pos4 && (!(*env)->GetDirectBufferAddress(env, pos4) || (*env)->GetDirectBufferCapacity(env, pos4) < need)) ||
+        (vel4 && (!(*env)->GetDirectBufferAddress(env, vel4) || (*env)->GetDirectBufferCapacity(env, vel4) < need)))
+        return BH_ERR_ARG; /* not direct, or too small for nbodies float4 */
     return bh_copy_vertices((bh_sim *)(intptr_t)sim, pos4 ? (float *)(*env)->GetDirectBufferAddress(env, pos4) : NULL,
                             vel4 ? (float *)(*env)->GetDirectBufferAddress(env, vel4) : NULL);
 }
