@@ -48,7 +48,7 @@ def lib():
         for name in ("bho_bounding_box", "bho_summarize", "bho_sort", "bho_integrate"):
             getattr(_LIB, name).restype = None
             getattr(_LIB, name).argtypes = [C.POINTER(_State)]
-        for name in ("bho_build_tree", "bho_calculate_force"):
+        for name in ("bho_build_tree", "bho_build_tree_parallel", "bho_calculate_force"):
             getattr(_LIB, name).restype = C.c_int32
             getattr(_LIB, name).argtypes = [C.POINTER(_State)]
         _LIB.bho_calculate_force_range.restype = C.c_int32
@@ -123,6 +123,7 @@ class OracleSim:
     # the six kernels, GPUBH:258-263
     def bounding_box(self): self.lib.bho_bounding_box(C.byref(self.state))
     def build_tree(self): return self.lib.bho_build_tree(C.byref(self.state))
+    def build_tree_parallel(self): return self.lib.bho_build_tree_parallel(C.byref(self.state))
     def summarize(self): self.lib.bho_summarize(C.byref(self.state))
     def sort(self): self.lib.bho_sort(C.byref(self.state))
     def calculate_force(self): return self.lib.bho_calculate_force(C.byref(self.state))

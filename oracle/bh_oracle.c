@@ -179,6 +179,89 @@ int32_t bho_build_tree(bho_state *s) {
     return 0;
 }
 
+/* buildtree.cl:42-199 as the reference runs it: bodies inserted CONCURRENTLY (OpenMP threads in place of work-items),
+ * a child slot locked with compare-and-swap to -2 while a leaf is split (:93-101), cells taken from `bottom` with an atomic
+ * decrement (:109), the finished sub-tree published into the locked slot after a fence (:173-180).  The tree SHAPE is the
+ * one bho_build_tree produces; cell numbers depend on the race, as in the reference.  Used for the CPU baseline
+ * (bench.py), where a single-threaded build would be a third of the step; the tests use both. */
+int32_t bho_build_tree_parallel(bho_state *s) {
+    const int n = s->n, m = s->m;
+    int32_t *child = s->child;
+    const float radius = *s->radius;
+    const float rootX = s->posX[m], rootY = s->posY[m], rootZ = s->posZ[m];
+    int globalMaxDepth = 1, failed = 0;
+#pragma omp parallel for schedule(dynamic, 2048) reduction(max : globalMaxDepth)
+    for (int body = 0; body < n; ++body) {
+        if (__atomic_load_n(&failed, __ATOMIC_RELAXED)) continue;
+        const float bx = s->posX[body], by = s->posY[body], bz = s->posZ[body];
+        int node = m, depth = 1;
+        float r = radius;
+        int path = (rootX < bx ? 1 : 0) + (rootY < by ? 2 : 0) + (rootZ < bz ? 4 : 0);   /* :65-68, strict < */
+        for (;;) {
+            int32_t *slot = &child[8 * (int64_t)node + path];
+            int ch = __atomic_load_n(slot, __ATOMIC_ACQUIRE);
+            while (ch >= n) {                               /* :77-89 */
+                node = ch; ++depth; r *= 0.5f;
+                path = (s->posX[node] < bx ? 1 : 0) + (s->posY[node] < by ? 2 : 0) + (s->posZ[node] < bz ? 4 : 0);
+                slot = &child[8 * (int64_t)node + path];
+                ch = __atomic_load_n(slot, __ATOMIC_ACQUIRE);
+            }
+            if (ch == -2) {                                 /* locked by another inserter: look again (:93) */
+                if (__atomic_load_n(&failed, __ATOMIC_RELAXED)) break;
+                continue;
+            }
+            int expected = ch;
+            if (!__atomic_compare_exchange_n(slot, &expected, -2, 0, __ATOMIC_ACQUIRE, __ATOMIC_RELAXED)) continue;
+            if (ch == -1) {                                 /* :98-101 */
+                __atomic_store_n(slot, body, __ATOMIC_RELEASE);
+                break;
+            }
+            int patch = -1, ok = 1;                         /* :102-180 */
+            int cur = node, curPath = path;
+            do {
+                depth++;
+                const int cell = __atomic_fetch_sub(s->bottom, 1, __ATOMIC_RELAXED) - 1;   /* :109 */
+                if (cell <= n) {                            /* :112-119 */
+                    __atomic_store_n(&failed, 1, __ATOMIC_RELAXED);
+                    ok = 0;
+                    break;
+                }
+                if (cell > patch) patch = cell;
+                float x = (float)(curPath & 1) * r;          /* :124-126 */
+                float y = (float)((curPath >> 1) & 1) * r;
+                float z = (float)((curPath >> 2) & 1) * r;
+                r *= 0.5f;
+                s->mass[cell] = -1.0f;                      /* :131-132 */
+                s->start[cell] = -1;
+                x = s->posX[cell] = s->posX[cur] - r + x;    /* :134-136, left to right */
+                y = s->posY[cell] = s->posY[cur] - r + y;
+                z = s->posZ[cell] = s->posZ[cur] - r + z;
+                for (int k = 0; k < 8; ++k) child[8 * (int64_t)cell + k] = -1;
+                if (patch != cell) child[8 * (int64_t)cur + curPath] = cell;   /* :141-146 */
+                const int qp = (x < s->posX[ch] ? 1 : 0) + (y < s->posY[ch] ? 2 : 0) + (z < s->posZ[ch] ? 4 : 0);   /* :148-152 */
+                child[8 * (int64_t)cell + qp] = ch;
+                cur = cell;                                 /* :155-161 */
+                curPath = (x < bx ? 1 : 0) + (y < by ? 2 : 0) + (z < bz ? 4 : 0);
+            } while (child[8 * (int64_t)cur + curPath] >= 0);
+            if (ok) {
+                child[8 * (int64_t)cur + curPath] = body;   /* :169 */
+                __atomic_store_n(slot, patch, __ATOMIC_RELEASE);   /* :173-180 */
+            } else {
+                __atomic_store_n(slot, ch, __ATOMIC_RELEASE);      /* give the leaf back; the error is reported below */
+            }
+            break;
+        }
+        if (depth > globalMaxDepth) globalMaxDepth = depth; /* :186 */
+    }
+    if (failed) {
+        *s->error = 1;
+        *s->bottom = m;
+        return 1;
+    }
+    if (globalMaxDepth > *s->maxDepth) *s->maxDepth = globalMaxDepth; /* atom_max, :199 */
+    return 0;
+}
+
 /* summarizetree.cl:55-178 in ascending cell order; children summed in octant
  * order (the reference's own order is timing dependent: ready children in
  * octant order, late ones in reverse arrival order, :93-111 vs :124-150). */

@@ -111,3 +111,34 @@ def test_oracle_ten_steps_of_the_bundled_universe(fma):
                          dt=float(g["dt"]), fma_policy=fma)
     assert o.step(10) == 0
     gc.check_trajectory(o.buf, g)
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 1000, 50000])
+def test_parallel_build_gives_the_same_tree(n):
+    """bho_build_tree_parallel (concurrent insertion with CAS-locked child slots, buildtree.cl:93-180 as the reference runs
+    it; the CPU baseline of bench.py) builds the tree of the sequential restatement: same canonical structure, same
+    cell count and depth, hence the same sorted order and bit-identical centres of mass."""
+    import oracle
+    from gpu_nbody_b200 import universe as U
+    a = U.generate_arrays(U.TwoDiskGalaxiesGenerator(7, 8) if n > 100 else U.PlummerUniverseGenerator(7), n)
+    oracle.lib().bho_set_num_threads(4)
+    seq, par = oracle.OracleSim(n, *a), oracle.OracleSim(n, *a)
+    for o, build in ((seq, seq.build_tree), (par, par.build_tree_parallel)):
+        o.bounding_box()
+        assert build() == 0
+    assert seq.bottom[0] == par.bottom[0] and seq.maxDepth[0] == par.maxDepth[0]
+    so, sc = oracle.canonicalize(seq.child, n, seq.m)
+    po, pc = oracle.canonicalize(par.child, n, par.m)
+    assert np.array_equal(sc, pc)
+    for o in (seq, par):
+        o.summarize(); o.sort()
+    assert np.array_equal(seq.sorted[:n], par.sorted[:n])
+    for k in ("posX", "posY", "posZ", "mass"):
+        assert np.array_equal(seq.buf[k][so].view(np.uint32), par.buf[k][po].view(np.uint32))
+    # coincident bodies exhaust the pool in both (buildtree.cl:112-119)
+    if n >= 17:
+        for k in range(3):
+            a[k][5] = a[k][3]
+        bad = oracle.OracleSim(n, *a)
+        bad.bounding_box()
+        assert bad.build_tree_parallel() == 1 and bad.error[0] == 1
