@@ -81,6 +81,7 @@ def load():
         "bh_set_graph": (C.c_int, [p, i32]),
         "bh_upload": (C.c_int, [p] + [p] * 7),
         "bh_upload_device": (C.c_int, [p] + [p] * 7),
+        "bh_upload_async": (C.c_int, [p] + [p] * 7),
         "bh_bounding_box": (C.c_int, [p]),
         "bh_build_tree": (C.c_int, [p]),
         "bh_summarize": (C.c_int, [p]),
@@ -108,6 +109,8 @@ def load():
         "bh_read": (C.c_int, [p, i32, p, i64]),
         "bh_buffer_length": (i64, [p, i32]),
         "bh_copy_vertices": (C.c_int, [p, p, p]),
+        "bh_copy_vertices_async": (C.c_int, [p, p, p]),
+        "bh_wait_copies": (C.c_int, [p]),
         "bh_stats": (C.c_int, [p, C.POINTER(BhStats)]),
         "bh_diagnostics": (C.c_int, [p, i32, C.POINTER(BhDiag)]),
         "bh_generate_universe": (C.c_int, [p, i32, C.c_uint64, f32, f32, f32]),

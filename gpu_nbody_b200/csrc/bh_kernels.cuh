@@ -1148,16 +1148,23 @@ __global__ void barrier_kernel(const PeerFlags pf, unsigned long long *seq, Scal
 }
 
 // ---- host-boundary helpers: pack uploads, export logical buffers -------------------
-__global__ void pack_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
-                            const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
-                            const float *__restrict__ mass, float4 *__restrict__ body4, float4 *__restrict__ velacc,
-                            int *__restrict__ perm, int n) {
+// positions + masses (what the tree stages and the walk read), and velocities + the host's numbering (what only the
+// finish pass reads): two kernels so that an asynchronous upload can deliver the second half while the step already runs
+__global__ void pack_pos_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                                const float *__restrict__ mass, float4 *__restrict__ body4, float4 *__restrict__ velacc,
+                                int *__restrict__ perm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     body4[i] = make_float4(x[i], y[i], z[i], mass[i]);
-    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], __int_as_float(i));
     velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     perm[i] = 0;
+}
+
+__global__ void pack_vel_kernel(const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                                float4 *__restrict__ velacc, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], __int_as_float(i));
 }
 
 // Logical float buffers (GPUBH:198-205): bodies 0..n-1 in the host's numbering, cells n..m; `which`: 0-2 pos,

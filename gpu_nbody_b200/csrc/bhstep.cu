@@ -44,6 +44,18 @@ struct Sim {
     bh::Scalars *hostSc = nullptr;  // pinned mirror
     void *staging = nullptr;
     size_t stagingBytes = 0;
+    // asynchronous vertex read-back (bh_copy_vertices_async): own staging, own stream, so that the device -> host copy of one
+    // step's vertices overlaps the next upload (other PCIe direction) and the next step
+    float4 *vtxStaging = nullptr;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evExported = nullptr, evCopied = nullptr;
+    bool copyPending = false;
+    float *deferredPos = nullptr, *deferredVel = nullptr;  // exported, but the device -> host copies are not enqueued yet
+    bool copyDeferred = false;
+    // asynchronous upload (bh_upload_async): the velocities travel on a second stream while the step's tree stages and walk run
+    cudaStream_t upStream = nullptr;
+    cudaEvent_t evPosReady = nullptr, evVelReady = nullptr, evPosArrived = nullptr;
+    bool velPending = false;
     int cur = 0;           // buffers holding the current body state
     int treePhase = 0;     // buffers the tree (child[]) was built from
     bool havePerm = false;   // a sort has run since the upload
@@ -106,6 +118,30 @@ int ensureStaging(Sim *s, size_t bytes) {
     s->stagingBytes = 0;
     BH_CUDA(s, cudaMalloc(&s->staging, bytes));
     s->stagingBytes = bytes;
+    return BH_OK;
+}
+
+// An asynchronous upload may still be delivering the velocities: everything that touches them waits for it (stream order)
+int settleVel(Sim *s) {
+    if (s->velPending) {
+        BH_CUDA(s, cudaStreamWaitEvent(s->stream, s->evVelReady, 0));
+        s->velPending = false;
+    }
+    return BH_OK;
+}
+
+// bh_copy_vertices_async exports at once but enqueues its device -> host copies lazily: if an upload follows, they start
+// behind that upload's position copies (which gate the next step) instead of competing with them for the link
+int flushCopy(Sim *s, cudaEvent_t after) {
+    if (!s->copyDeferred) return BH_OK;
+    const size_t bytes = sizeof(float4) * (size_t)s->n;
+    BH_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->evExported, 0));
+    if (after) BH_CUDA(s, cudaStreamWaitEvent(s->copyStream, after, 0));
+    if (s->deferredPos) BH_CUDA(s, cudaMemcpyAsync(s->deferredPos, s->vtxStaging, bytes, cudaMemcpyDeviceToHost, s->copyStream));
+    if (s->deferredVel) BH_CUDA(s, cudaMemcpyAsync(s->deferredVel, s->vtxStaging + s->n, bytes, cudaMemcpyDeviceToHost, s->copyStream));
+    BH_CUDA(s, cudaEventRecord(s->evCopied, s->copyStream));
+    s->copyDeferred = false;
+    s->copyPending = true;
     return BH_OK;
 }
 
@@ -239,6 +275,8 @@ int launchStage(Sim *s, int stage, bool fused) {
         const bool sliced = fused && s->p2p;
         launchWalk(s, sliced ? s->sliceFirst : 0, sliced ? s->sliceCount : n, sliced);
         if (!fused) {
+            int rc = settleVel(s);
+            if (rc) return rc;
             const unsigned stride = s->p2p ? (unsigned)accStride(s) : 0u;
             bh::apply_acc_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->acc, stride, s->permValid ? s->perm : nullptr,
                                                                        s->velacc[s->cur], s->sc, n, s->dt);
@@ -246,7 +284,9 @@ int launchStage(Sim *s, int stage, bool fused) {
         break;
     }
     case BH_STAGE_INTEGRATE: {
-        int rc = launchFinish(s, fused);
+        int rc = settleVel(s);
+        if (rc) return rc;
+        rc = launchFinish(s, fused);
         if (rc) return rc;
         break;
     }
@@ -355,9 +395,11 @@ int graphStep(Sim *s) {
 }
 
 int stepAsync(Sim *s, int nsteps) {
+    int rcf = flushCopy(s, nullptr);
+    if (rcf) return rcf;
     for (int i = 0; i < nsteps; ++i) {
         // (the legacy default stream cannot be captured)
-        if (s->useGraph && !s->profiling && !s->counting && s->stream != nullptr) {
+        if (s->useGraph && !s->profiling && !s->counting && !s->velPending && s->stream != nullptr) {
             int rc = graphStep(s);
             if (rc == BH_OK) continue;
             if (s->useGraph) return rc;  // a real failure; otherwise capture was refused and the graph is now off
@@ -533,7 +575,10 @@ void bh_destroy(bh_sim *sim) {
     if (!sim) return;
     Sim *s = S(sim);
     cudaSetDevice(s->device);
+    flushCopy(s, nullptr);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copyStream) cudaStreamSynchronize(s->copyStream);
+    if (s->upStream) cudaStreamSynchronize(s->upStream);
     dropGraphs(s);
     closePeers(s);
     for (int b = 0; b < 2; ++b) { cudaFree(s->body4[b]); cudaFree(s->velacc[b]); }
@@ -544,6 +589,14 @@ void bh_destroy(bh_sim *sim) {
     if (s->evCreated)
         for (auto &row : s->ev)
             for (auto &e : row) cudaEventDestroy(e);
+    cudaFree(s->vtxStaging);
+    if (s->evExported) cudaEventDestroy(s->evExported);
+    if (s->evCopied) cudaEventDestroy(s->evCopied);
+    if (s->copyStream) cudaStreamDestroy(s->copyStream);
+    if (s->evPosReady) cudaEventDestroy(s->evPosReady);
+    if (s->evVelReady) cudaEventDestroy(s->evVelReady);
+    if (s->evPosArrived) cudaEventDestroy(s->evPosArrived);
+    if (s->upStream) cudaStreamDestroy(s->upStream);
     if (s->ownStream) cudaStreamDestroy(s->ownStream);
     delete s;
 }
@@ -553,6 +606,10 @@ void bh_destroy(bh_sim *sim) {
     Sim *s = S(sim);                                           \
     BH_CUDA(s, cudaSetDevice(s->device))
 
+#define BH_ENTER_SETTLED(sim)                                  \
+    BH_ENTER(sim);                                             \
+    do { int rcv_ = settleVel(s); if (rcv_) return rcv_; } while (0)
+
 int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
     BH_ENTER(sim);
     dropGraphs(s);  // kernel arguments change
@@ -561,14 +618,14 @@ int bh_set_theta_macro(bh_sim *sim, float theta_macro) {
 }
 
 int bh_set_stream(bh_sim *sim, void *cuda_stream) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     s->stream = reinterpret_cast<cudaStream_t>(cuda_stream);  // NULL = CUDA's default stream, as everywhere in CUDA
     return BH_OK;
 }
 
 int bh_use_private_stream(bh_sim *sim) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     s->stream = s->ownStream;
     return BH_OK;
@@ -615,27 +672,55 @@ int bh_set_vertex_buffers(bh_sim *sim, void *pos4_device, void *vel4_device) {
     return BH_OK;
 }
 
-static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind) {
+// deferVel: the velocities are copied and packed on a second stream; the call returns without waiting for anything
+static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bool deferVel) {
     for (int i = 0; i < 7; ++i)
         if (!src[i]) return fail(s, BH_ERR_ARG, "NULL input array %d", i);
+    int rc = settleVel(s);  // a previous asynchronous upload still owns the staging buffer
+    if (rc) return rc;
     const size_t n = s->n;
+    const int grid = (s->n + 255) / 256;
     const float *dev[7];
+    static const int order[7] = {0, 1, 2, 6, 3, 4, 5};  // positions and masses first
     if (kind == cudaMemcpyHostToDevice) {
-        int rc = ensureStaging(s, sizeof(float) * 7 * n);
+        rc = ensureStaging(s, sizeof(float) * 7 * n);
         if (rc) return rc;
         float *stg = static_cast<float *>(s->staging);
-        for (int i = 0; i < 7; ++i) {
-            BH_CUDA(s, cudaMemcpyAsync(stg + i * n, src[i], sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        if (deferVel && !s->upStream) {
+            BH_CUDA(s, cudaStreamCreateWithFlags(&s->upStream, cudaStreamNonBlocking));
+            BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosReady, cudaEventDisableTiming));
+            BH_CUDA(s, cudaEventCreateWithFlags(&s->evVelReady, cudaEventDisableTiming));
+        }
+        if (!s->evPosArrived) BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosArrived, cudaEventDisableTiming));
+        for (int k = 0; k < 7; ++k) {
+            const int i = order[k];
+            cudaStream_t st = (deferVel && k >= 4) ? s->upStream : s->stream;
+            BH_CUDA(s, cudaMemcpyAsync(stg + i * n, src[i], sizeof(float) * n, cudaMemcpyHostToDevice, st));
             dev[i] = stg + i * n;
+            if (k == 3) {
+                // the position copies gate the next step: the velocity copies (second stream) and a pending vertex
+                // read-back (third stream) start behind them instead of sharing the link with them
+                BH_CUDA(s, cudaEventRecord(s->evPosArrived, s->stream));
+                if (deferVel) BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evPosArrived, 0));
+                rc = flushCopy(s, s->evPosArrived);
+                if (rc) return rc;
+            }
         }
     } else {
         for (int i = 0; i < 7; ++i) dev[i] = src[i];
+        deferVel = false;
     }
-    int rc = resetState(s);
+    rc = resetState(s);
     if (rc) return rc;
-    bh::pack_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], s->body4[0],
-                                                              s->velacc[0], s->perm, s->n);
+    bh::pack_pos_kernel<<<grid, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[6], s->body4[0], s->velacc[0], s->perm, s->n);
     BH_CUDA(s, cudaGetLastError());
+    bh::pack_vel_kernel<<<grid, 256, 0, deferVel ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], s->n);
+    BH_CUDA(s, cudaGetLastError());
+    if (deferVel) {
+        BH_CUDA(s, cudaEventRecord(s->evVelReady, s->upStream));
+        s->velPending = true;
+        return BH_OK;
+    }
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     return BH_OK;
 }
@@ -644,14 +729,21 @@ int bh_upload(bh_sim *sim, const float *x, const float *y, const float *z, const
               const float *vz, const float *mass) {
     BH_ENTER(sim);
     const float *src[7] = {x, y, z, vx, vy, vz, mass};
-    return uploadImpl(s, src, cudaMemcpyHostToDevice);
+    return uploadImpl(s, src, cudaMemcpyHostToDevice, false);
+}
+
+int bh_upload_async(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+                    const float *vz, const float *mass) {
+    BH_ENTER(sim);
+    const float *src[7] = {x, y, z, vx, vy, vz, mass};
+    return uploadImpl(s, src, cudaMemcpyHostToDevice, true);
 }
 
 int bh_upload_device(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
                      const float *vz, const float *mass) {
     BH_ENTER(sim);
     const float *src[7] = {x, y, z, vx, vy, vz, mass};
-    return uploadImpl(s, src, cudaMemcpyDeviceToDevice);
+    return uploadImpl(s, src, cudaMemcpyDeviceToDevice, false);
 }
 
 int bh_bounding_box(bh_sim *sim) { BH_ENTER(sim); return singleStage(s, BH_STAGE_BBOX); }
@@ -716,7 +808,7 @@ int bh_peer_barrier(bh_sim *sim) {
 }
 
 int bh_apply_acceleration(bh_sim *sim) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     const unsigned stride = s->p2p ? (unsigned)accStride(s) : 0u;
     bh::apply_acc_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->acc, stride, s->permValid ? s->perm : nullptr, s->velacc[s->cur],
                                                                    s->sc, s->n, s->dt);
@@ -726,7 +818,7 @@ int bh_apply_acceleration(bh_sim *sim) {
 }
 
 int bh_finish_async(bh_sim *sim) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     int rc = launchFinish(s, true);
     if (rc == BH_OK) s->stageLaunches[BH_STAGE_INTEGRATE]++;
     return rc;
@@ -803,7 +895,7 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which) {
 }
 
 int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     const int64_t len = bh_buffer_length(sim, which);
     if (len < 0) return fail(s, BH_ERR_ARG, "unknown buffer %d", which);
     if (!dst || count < 0 || count > len) return fail(s, BH_ERR_ARG, "bad destination/count for buffer %d", which);
@@ -865,7 +957,7 @@ int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
 }
 
 int bh_copy_vertices_device(bh_sim *sim, void *pos4_device, void *vel4_device) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     if (!pos4_device && !vel4_device) return BH_OK;
     bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], static_cast<float4 *>(pos4_device),
                                                                        static_cast<float4 *>(vel4_device), s->n);
@@ -873,28 +965,48 @@ int bh_copy_vertices_device(bh_sim *sim, void *pos4_device, void *vel4_device) {
     return BH_OK;
 }
 
-int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4) {
-    BH_ENTER(sim);
+int bh_copy_vertices_async(bh_sim *sim, float *pos4, float *vel4) {
+    BH_ENTER_SETTLED(sim);
     if (!pos4 && !vel4) return BH_OK;
     const size_t bytes = sizeof(float4) * (size_t)s->n;
-    int rc = ensureStaging(s, 2 * bytes);
-    if (rc) return rc;
-    float4 *dp = static_cast<float4 *>(s->staging), *dv = dp + s->n;
-    // the position half travels while the velocity half is still being written
-    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], pos4 ? dp : nullptr, nullptr, s->n);
-    BH_CUDA(s, cudaGetLastError());
-    if (pos4) BH_CUDA(s, cudaMemcpyAsync(pos4, dp, bytes, cudaMemcpyDeviceToHost, s->stream));
-    if (vel4) {
-        bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], nullptr, dv, s->n);
-        BH_CUDA(s, cudaGetLastError());
-        BH_CUDA(s, cudaMemcpyAsync(vel4, dv, bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (!s->vtxStaging) {
+        BH_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->vtxStaging), 2 * bytes));
+        BH_CUDA(s, cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+        BH_CUDA(s, cudaEventCreateWithFlags(&s->evExported, cudaEventDisableTiming));
+        BH_CUDA(s, cudaEventCreateWithFlags(&s->evCopied, cudaEventDisableTiming));
     }
-    BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    int rc = flushCopy(s, nullptr);  // an earlier export that nobody has waited for
+    if (rc) return rc;
+    if (s->copyPending) BH_CUDA(s, cudaStreamWaitEvent(s->stream, s->evCopied, 0));  // the staging buffer is still being read
+    float4 *dp = s->vtxStaging, *dv = dp + s->n;
+    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], pos4 ? dp : nullptr,
+                                                                       vel4 ? dv : nullptr, s->n);
+    BH_CUDA(s, cudaGetLastError());
+    BH_CUDA(s, cudaEventRecord(s->evExported, s->stream));
+    s->deferredPos = pos4;
+    s->deferredVel = vel4;
+    s->copyDeferred = true;
     return BH_OK;
 }
 
-int bh_stats(bh_sim *sim, bh_stats_t *out) {
+int bh_wait_copies(bh_sim *sim) {
     BH_ENTER(sim);
+    int rc = flushCopy(s, nullptr);
+    if (rc) return rc;
+    if (s->copyPending) {
+        BH_CUDA(s, cudaEventSynchronize(s->evCopied));
+        s->copyPending = false;
+    }
+    return BH_OK;
+}
+
+int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4) {
+    int rc = bh_copy_vertices_async(sim, pos4, vel4);
+    return rc ? rc : bh_wait_copies(sim);
+}
+
+int bh_stats(bh_sim *sim, bh_stats_t *out) {
+    BH_ENTER_SETTLED(sim);
     if (!out) return fail(s, BH_ERR_ARG, "out is NULL");
     BH_CUDA(s, cudaMemcpyAsync(s->hostSc, s->sc, sizeof(bh::Scalars), cudaMemcpyDeviceToHost, s->stream));
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -929,7 +1041,7 @@ int bh_reset_stats(bh_sim *sim) {
 int32_t bh_number_of_bodies(bh_sim *sim) { return sim ? S(sim)->n : BH_ERR_ARG; }
 
 int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, float p1, float p2) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     if (kind < 0 || kind > 2) return fail(s, BH_ERR_ARG, "unknown universe kind %d", kind);
     int rc = resetState(s);
     if (rc) return rc;
@@ -940,7 +1052,7 @@ int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, flo
 }
 
 int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     if (!out) return fail(s, BH_ERR_ARG, "out is NULL");
     int rc = ensureStaging(s, 8 * sizeof(double));
     if (rc) return rc;
@@ -1049,11 +1161,11 @@ int bh_upload_universe_file(bh_sim *sim, const char *path) {
     if (!readUniverse(path, false, s->n, u)) return fail(s, BH_ERR_ARG, "%s", u.error.c_str());
     const float *src[7];
     for (int a = 0; a < 7; ++a) src[a] = u.arrays[a].data();
-    return uploadImpl(s, src, cudaMemcpyHostToDevice);
+    return uploadImpl(s, src, cudaMemcpyHostToDevice, false);
 }
 
 int bh_write_universe_file(bh_sim *sim, const char *path) {
-    BH_ENTER(sim);
+    BH_ENTER_SETTLED(sim);
     if (!path) return fail(s, BH_ERR_ARG, "path is NULL");
     const size_t n = s->n;
     int rc = ensureStaging(s, sizeof(float) * 7 * n);

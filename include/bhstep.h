@@ -120,6 +120,12 @@ int bh_set_graph(bh_sim *sim, int32_t on);
  * reset to their initial values (step=-1, maxDepth=1, rest 0). */
 int bh_upload(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
               const float *vz, const float *mass);
+/* The same without waiting, for pinned host arrays: positions and masses are copied on the simulation's stream, the
+ * velocities on a second one, and the next bh_step starts its tree stages and force walk as soon as the former have
+ * arrived (only its last pass needs the velocities).  The arrays must stay valid and unchanged until a call that
+ * waits for the device returns (bh_step, bh_check, bh_read ...). */
+int bh_upload_async(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
+                    const float *vz, const float *mass);
 /* Same with device pointers (inputs already resident in HBM). */
 int bh_upload_device(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
                      const float *vz, const float *mass);
@@ -180,6 +186,11 @@ int64_t bh_buffer_length(bh_sim *sim, int32_t which);
 /* kernels/nbody/copyvertices.cl:8-17 with host destinations: pos4[i] = {x,y,z,1},
  * vel4[i] = {vx,vy,vz,1}, i < nbodies.  Either pointer may be NULL. */
 int bh_copy_vertices(bh_sim *sim, float *pos4, float *vel4);
+/* The same without waiting: the vertices are exported on the simulation's stream and copied to the (pinned) host buffers
+ * on a second stream, so the read-back overlaps whatever the caller enqueues next -- the next bh_upload (other PCIe
+ * direction), the next bh_step.  The host buffers are valid after bh_wait_copies (or the next bh_copy_vertices*). */
+int bh_copy_vertices_async(bh_sim *sim, float *pos4, float *vel4);
+int bh_wait_copies(bh_sim *sim);
 /* The same with DEVICE destinations (float4[nbodies] each) -- what a CUDA-mapped OpenGL vertex buffer is
  * (cudaGraphicsResourceGetMappedPointer; GPUBH:230-246 createFromGLBuffer + :253-256 acquire): async on the
  * simulation's stream, no host staging. */

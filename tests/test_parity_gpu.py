@@ -203,6 +203,53 @@ def test_vertex_buffers_on_the_device():
     sim.close()
 
 
+def test_async_vertex_readback_overlapping_the_next_upload():
+    """bh_copy_vertices_async + bh_wait_copies: the read-back of one step's vertices is still in flight while the next
+    upload and step are enqueued (bench.py's e2e loop); what arrives is that step's state, not the next one's."""
+    import torch
+    n = 300_000
+    a = gen(U.PlummerUniverseGenerator(31), n)
+    b = gen(U.PlummerUniverseGenerator(32), n)
+    sim, _ = parity.make_pair(a, counting=False)
+    lib = sim._lib
+    sim.step(1)
+    want_p, want_v = [x.copy() for x in sim.copyVertices()]
+    sim.upload(*a)
+    sim.step(1)
+    pos4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    vel4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    sim._check(lib.bh_copy_vertices_async(sim.handle, pos4.data_ptr(), vel4.data_ptr()))
+    sim.upload(*b)          # a different universe goes up while the vertices come down
+    sim.step(1)
+    sim._check(lib.bh_wait_copies(sim.handle))
+    assert np.array_equal(pos4.numpy(), want_p) and np.array_equal(vel4.numpy(), want_v)
+    sim.close()
+
+
+def test_async_upload_equals_upload():
+    """bh_upload_async (velocities arrive on a second stream while the step's tree stages and walk already run) leaves
+    the same state as bh_upload, whether a step or a read follows it."""
+    import torch
+    n = 200_000
+    a = gen(U.TwoDiskGalaxiesGenerator(5, 6), n)
+    ref, _ = parity.make_pair(a, counting=False)
+    ref.step(2)
+    want = {k: ref.readBuffer(k, n) for k in ("posX", "velX", "velZ", "accY", "sorted")}
+    ref.close()
+    pinned = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in a]
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+    sim.init(None)
+    lib = sim._lib
+    for _ in range(2):   # the second round overwrites a stepped state
+        sim._check(lib.bh_upload_async(sim.handle, *(p.data_ptr() for p in pinned)))
+        assert np.array_equal(sim.readBuffer("velY", n).view(np.uint32), a[4].view(np.uint32))   # a read waits for the velocities
+        sim._check(lib.bh_upload_async(sim.handle, *(p.data_ptr() for p in pinned)))
+        sim.step(2)
+        for k, w in want.items():
+            assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), w.view(np.uint32)), k
+    sim.close()
+
+
 def test_native_universe_writer(tmp_path):
     """bh_write_universe_file == UniverseSerializer.serialize of the current state: readable by the Python reader
     (same wire format as the reference's files, test_host.py) and by the native loader; a restart from the dump
