@@ -663,7 +663,7 @@ struct WalkShared {
     int2 meta[kWalkWarps][kWalkGroups][kWalkSlots + 1];
 };
 
-template <bool COUNT>
+template <bool COUNT, bool POT>
 __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ octet,
                                                                             const int2 *__restrict__ ometa, const int *__restrict__ perm,
                                                                             const PeerBuffers dst, Scalars *sc, int *__restrict__ spill, int n,
@@ -709,14 +709,15 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
     int k0 = 0, nact = 0;
     float2 npxA = make_float2(0.f, 0.f), npyA = npxA, npzA = npxA, npxB = npxA, npyB = npxA, npzB = npxA;
     float2 axA = npxA, ayA = npxA, azA = npxA, axB = npxA, ayB = npxA, azB = npxA;
+    float2 potA = npxA, potB = npxA;  // POT: sum of m / sqrt(r^2 + eps) over the nodes used (the tree's potential, self term included)
     unsigned long long nInter = 0, nOpen = 0;
     for (;;) {
         // ---- group slots: finished walks write their accelerations and take the next group ---------------------
         const bool finished = active && stkTop == stkBase && qTop == qBase && spilled == 0;
         if (__any_sync(kFull, finished || fetch)) {
             if (finished) {
-                const float4 a[4] = {make_float4(axA.x, ayA.x, azA.x, 0.f), make_float4(axA.y, ayA.y, azA.y, 0.f),
-                                     make_float4(axB.x, ayB.x, azB.x, 0.f), make_float4(axB.y, ayB.y, azB.y, 0.f)};
+                const float4 a[4] = {make_float4(axA.x, ayA.x, azA.x, potA.x), make_float4(axA.y, ayA.y, azA.y, potA.y),
+                                     make_float4(axB.x, ayB.x, azB.x, potB.x), make_float4(axB.y, ayB.y, azB.y, potB.y)};
                 for (int r = 0; r < dst.count; ++r) {  // own buffer, then the peers' (NVLink stores)
                     float4 *out = dst.buf[r] + phase + k0;
 #pragma unroll
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                     }
                     npxA = make_float2(-p[0].x, -p[1].x); npyA = make_float2(-p[0].y, -p[1].y); npzA = make_float2(-p[0].z, -p[1].z);
                     npxB = make_float2(-p[2].x, -p[3].x); npyB = make_float2(-p[2].y, -p[3].y); npzB = make_float2(-p[2].z, -p[3].z);
-                    axA = ayA = azA = axB = ayB = azB = make_float2(0.f, 0.f);
+                    axA = ayA = azA = axB = ayB = azB = potA = potB = make_float2(0.f, 0.f);
                     sts_s32(stkBase, rootEntry);
                     stkTop = stkBase + 4;
                     qTop = qBase;
@@ -849,6 +850,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                 const float2 fB = __fmul2_rn(__fmul2_rn(__fmul2_rn(rinvB, rinvB), rinvB), mw2);
                 axA = __ffma2_rn(dxA, fA, axA); ayA = __ffma2_rn(dyA, fA, ayA); azA = __ffma2_rn(dzA, fA, azA);  // :149-151
                 axB = __ffma2_rn(dxB, fB, axB); ayB = __ffma2_rn(dyB, fB, ayB); azB = __ffma2_rn(dzB, fB, azB);
+                if (POT) {
+                    potA = __ffma2_rn(mw2, rinvA, potA);
+                    potB = __ffma2_rn(mw2, rinvB, potB);
+                }
                 if (open) {  // all lanes of the group store the same entry to the same address
                     sts_s32(stkTop, lds_s32(entAddr));
                     stkTop += 4;
@@ -1374,6 +1379,24 @@ __global__ void __launch_bounds__(kPotTile) potential_kernel(const float4 *__res
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out + 5, e);
 }
+
+// Tree potential (bh_diagnostics mode 2): the walk's POT variant leaves S_k = sum_j m_j / sqrt(r_kj^2 + eps) over the nodes
+// it used -- the body itself included, at r = 0 -- in acc[k].w; out[5] += -1/2 sum_k m_k (S_k - m_k / sqrt(eps)).
+__global__ void __launch_bounds__(256) tree_potential_kernel(const float4 *__restrict__ body4, const int *__restrict__ perm,
+                                                             const float4 *__restrict__ acc, unsigned phaseStride,
+                                                             const Scalars *__restrict__ sc, double *__restrict__ out, int n, float eps) {
+    const float4 *a = acc + (size_t)(sc->step & 1) * phaseStride;
+    const float selfInv = rsqrtf(eps);
+    double e = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const float m = body4[perm ? perm[k] : k].w;
+        e += -0.5 * (double)m * ((double)a[k].w - (double)m * (double)selfInv);
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + 5, e);
+}
+
+__global__ void adjust_step_kernel(Scalars *sc, int delta) { sc->step += delta; }
 
 // ---- measurement utility: FP32 FMA peak of the device (roofline denominator of the force kernel) ----
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {

@@ -176,7 +176,7 @@ bh::PeerBuffers accDestinations(const Sim *s, bool peers) {
 }
 
 // force walk for tree-order slots [first, first+cnt) into the acceleration buffer(s)
-void launchWalk(Sim *s, int first, int cnt, bool peers) {
+void launchWalk(Sim *s, int first, int cnt, bool peers, bool potential = false) {
     if (cnt <= 0) return;
     const bh::PeerBuffers dst = accDestinations(s, peers);
     const int *perm = s->permValid ? s->perm : nullptr;
@@ -187,10 +187,12 @@ void launchWalk(Sim *s, int first, int cnt, bool peers) {
         const int grid = std::max(1, std::min(s->walkGrid, (groups + 31) / 32));
         const size_t smem = sizeof(bh::WalkShared);
         cudaMemsetAsync(&s->sc->walkTicket, 0, sizeof(int), s->stream);
-        if (s->counting)
-            bh::walk_kernel<true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
+        if (potential)
+            bh::walk_kernel<false, true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
+        else if (s->counting)
+            bh::walk_kernel<true, false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         else
-            bh::walk_kernel<false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
+            bh::walk_kernel<false, false><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         return;
     }
     // 32-wide votes (not reference-exact), or the shared-stack walk on request
@@ -539,10 +541,11 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     // tiny problems: do not launch more waiting threads than there can be cells
     const int cellBlocks = (int)((nc + bh::kSummThreads - 1) / bh::kSummThreads);
     s->sortGrid = std::max(1, std::min(s->sortGrid, cellBlocks));
-    cudaFuncSetAttribute(bh::walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
-    cudaFuncSetAttribute(bh::walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
+    cudaFuncSetAttribute(bh::walk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
+    cudaFuncSetAttribute(bh::walk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
+    cudaFuncSetAttribute(bh::walk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bh::WalkShared));
     perSM = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::walk_kernel<false>, bh::kWalkThreads, sizeof(bh::WalkShared));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::walk_kernel<false, false>, bh::kWalkThreads, sizeof(bh::WalkShared));
     s->walkGrid = s->numSMs * std::max(1, std::min(perSM, bh::kWalkCtasPerSM));
     if ((e = cudaMalloc(reinterpret_cast<void **>(&s->spill), sizeof(int) * (size_t)s->walkGrid * bh::kWalkWarps * bh::kWalkGroups * bh::kWalkSpillCap)) != cudaSuccess)
         return bail(BH_ERR_ALLOC, "cudaMalloc spill", e);
@@ -1059,8 +1062,26 @@ int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out) {
     double *d = static_cast<double *>(s->staging);
     BH_CUDA(s, cudaMemsetAsync(d, 0, 8 * sizeof(double), s->stream));
     bh::kinetic_kernel<<<std::min((s->n + 255) / 256, s->numSMs * 8), 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], d, s->n);
-    if (with_potential)
+    if (with_potential == 1) {
         bh::potential_kernel<<<(s->n + bh::kPotTile - 1) / bh::kPotTile, bh::kPotTile, 0, s->stream>>>(s->body4[s->cur], d, s->n, s->eps);
+    } else if (with_potential == 2) {
+        // the tree's potential: tree stages + the walk's potential variant on the current positions; the bodies, the step
+        // counter and the accelerations of the state are left as they are (only the tree buffers and the scratch
+        // acceleration buffer are overwritten, as by the next step)
+        if (s->vote != 16) return fail(s, BH_ERR_ARG, "the tree potential needs vote_width 16");
+        const bool counting = s->counting;
+        s->counting = false;
+        int rcs = BH_OK;
+        for (int st = BH_STAGE_BBOX; st <= BH_STAGE_SORT && rcs == BH_OK; ++st) {
+            rcs = launchStage(s, st, true);
+            if (st == BH_STAGE_BBOX) bh::adjust_step_kernel<<<1, 1, 0, s->stream>>>(s->sc, -1);  // boundingbox.cl:195 counted a step
+        }
+        s->counting = counting;
+        if (rcs) return rcs;
+        launchWalk(s, 0, s->n, false, true);
+        bh::tree_potential_kernel<<<std::min((s->n + 255) / 256, s->numSMs * 8), 256, 0, s->stream>>>(
+            s->body4[s->cur], s->permValid ? s->perm : nullptr, s->acc, s->p2p ? (unsigned)accStride(s) : 0u, s->sc, d, s->n, s->eps);
+    }
     BH_CUDA(s, cudaGetLastError());
     double h[8];
     BH_CUDA(s, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));

@@ -167,7 +167,8 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
     def resetStats(self): self._check(self._lib.bh_reset_stats(self._sim))
 
     def diagnostics(self, with_potential=True):
-        """printEnergy / printImpulse (GPUBH:305-365) on the device: dict(ekin, epot, etot, px, py, pz, mass)."""
+        """printEnergy / printImpulse (GPUBH:305-365) on the device: dict(ekin, epot, etot, px, py, pz, mass).
+        with_potential: True / 1 = exact tiled O(N^2) sum, 2 = through the tree (one more force walk), False = none."""
         d = _lib.BhDiag()
         self._check(self._lib.bh_diagnostics(self._sim, int(with_potential), C.byref(d)))
         out = {k: getattr(d, k) for k, _ in d._fields_}

@@ -208,9 +208,11 @@ enum bh_universe_kind { BH_UNIVERSE_RANDOM_CUBIC = 0, BH_UNIVERSE_PLUMMER = 1, B
 int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, float p1, float p2);
 
 /* printEnergy / printImpulse (GPUBH:305-365) as device reductions instead of O(N^2) host loops:
- * kinetic energy, momentum, total mass, and -- if with_potential -- the softened potential
- * -sum_{i<j} m_i m_j / sqrt(r^2 + eps2) by a tiled direct sum (the parity tests' energy formula; the
- * reference's own printEnergy uses an unsoftened, doubled potential and is not reproduced). */
+ * kinetic energy, momentum, total mass, and the softened potential -sum_{i<j} m_i m_j / sqrt(r^2 + eps2)
+ * (the parity tests' energy formula; the reference's own printEnergy uses an unsoftened, doubled potential
+ * and is not reproduced): with_potential = 1 by a tiled direct sum (exact, O(N^2): up to ~10^5 bodies),
+ * = 2 through the tree (the force walk's opening rule applied to m / r instead of m d / r^3: one more walk,
+ * ~1e-3 relative; the state is not advanced), = 0 not at all. */
 typedef struct bh_diag_t { double ekin, epot, px, py, pz, mass; } bh_diag_t;
 int bh_diagnostics(bh_sim *sim, int32_t with_potential, bh_diag_t *out);
 

@@ -394,6 +394,34 @@ def test_device_diagnostics_match_host_energy():
     sim.close()
 
 
+def test_tree_potential_diagnostic():
+    """bh_diagnostics mode 2: the potential through the tree (what makes an energy-drift check affordable at 10^7 bodies)
+    agrees with the exact pair sum to the tree's accuracy and leaves the simulation state untouched."""
+    n = 30000
+    a = gen(U.PlummerUniverseGenerator(18), n)
+    sim, _ = parity.make_pair(a, counting=False)
+    twin, _ = parity.make_pair(a, counting=False)
+    sim.step(3); twin.step(3)
+    exact = sim.diagnostics(1)
+    before = {k: sim.readBuffer(k, n) for k in ("posX", "posZ", "velY", "accZ", "mass")}   # (the tree buffers, sorted[] included, are rebuilt)
+    step_before = sim.scalar("step")
+    tree = sim.diagnostics(2)
+    assert abs(tree["epot"] - exact["epot"]) <= 3e-3 * abs(exact["epot"]), (tree["epot"], exact["epot"])
+    assert abs(tree["ekin"] - exact["ekin"]) <= 1e-12 * exact["ekin"] and sim.scalar("step") == step_before
+    for k, v in before.items():
+        assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), v.view(np.uint32)), k
+    sim.step(2); twin.step(2)     # and the simulation goes on exactly as if nobody had looked
+    for k in ("posX", "velY", "accZ", "sorted"):
+        assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), twin.readBuffer(k, n).view(np.uint32)), k
+    # a million bodies: a few milliseconds instead of an O(N^2) sum; sanity against the virial expectation of the Plummer model
+    big = GPUBarnesHutNBodySimulation(Mode.DEFAULT, 1 << 20, None)
+    big.init(None)
+    big.generateOnDevice("plummer", 5)
+    d = big.diagnostics(2)
+    assert -0.7 < d["epot"] < -0.3 and 0.35 < 2 * d["ekin"] / abs(d["epot"]) < 1.3, d
+    big.close(); sim.close(); twin.close()
+
+
 def test_native_universe_file_upload(tmp_path):
     """bh_upload_universe_file == SerializedUniverseGenerator + loadBuffers, including the size check."""
     n = 3000
