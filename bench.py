@@ -355,20 +355,27 @@ def run_ours(args, rank, world, local_rank):
         vel4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            # pinned host arrays in (bh_upload_async: the step starts when positions and masses have arrived, the velocities
-            # follow while it runs), one step, float4 vertices out to pinned host buffers; the read-back of step i is
-            # asynchronous too (bh_copy_vertices_async) and overlaps the upload of step i + 1, which travels the other way
+            # pinned host arrays in (bh_upload_async: all copies on a second stream; the step starts when positions and
+            # masses have arrived, its last pass when the velocities have), one step (bh_step_async), float4 vertices out to
+            # pinned host buffers (bh_copy_vertices_async: read-back behind the next upload's position copies).  Nothing
+            # waits between steps, so the next step's inputs cross the link while the current step computes.
             sim._check(lib.bh_upload_async(sim.handle, *(p.data_ptr() for p in pinned)))
-            run.step(1)
+            if world == 1:
+                sim._check(lib.bh_step_async(sim.handle, 1))
+            else:
+                run.dsim.step_async(1)
+            run.steps_done += 1
             if rank == 0:
                 sim._check(lib.bh_copy_vertices_async(sim.handle, pos4.data_ptr(), vel4.data_ptr()))
         e2e_step()
         sim._check(lib.bh_wait_copies(sim.handle))
+        run.engine.check()
         run.barrier()
         t0 = time.perf_counter()
         for _ in range(K):
             e2e_step()
         sim._check(lib.bh_wait_copies(sim.handle))  # the last step's vertices have arrived
+        run.engine.check()                          # ... and every step ran without a device error
         run.barrier()
         t_e2e = run.max_over_ranks(time.perf_counter() - t0)
         line["e2e"] = {"value": n * K / t_e2e, "unit": "body-steps/s", "steps": K, "ms_per_step": 1e3 * t_e2e / K,

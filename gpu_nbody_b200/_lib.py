@@ -122,6 +122,7 @@ def load():
         "bh_number_of_nodes": (i32, [i32]),
         "bh_abi_version": (i32, []),
         "bh_measure_fp32_peak": (C.c_int, [i32, C.POINTER(C.c_double)]),
+        "bh_measure_fp32x2_rate": (C.c_int, [i32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

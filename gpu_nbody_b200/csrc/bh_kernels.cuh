@@ -1412,4 +1412,27 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
     if (r == 123.456f) out[0] = r;  // never true; keeps the chains alive
 }
 
+// The same with the instruction the walk is made of: FFMA2 (packed fp32x2) with three distinct register-pair operands per
+// instruction (no constants, no immediate, no operand reuse): what the register file lets the fp32 pipe sustain for real code.
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(float *out, int iters, float a, float b) {
+    float2 x[8], y[8], z[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        x[u] = make_float2(threadIdx.x + u, threadIdx.x - u);
+        y[u] = make_float2(a + 1e-7f * u, a - 1e-7f * u);
+        z[u] = make_float2(b * (u + 1), b * (u + 2));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ffma2_rn(x[u], y[(u + r) & 7], z[(u + 3 * r) & 7]);
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r += x[u].x + x[u].y;
+    if (r == 123.456f) out[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace bh

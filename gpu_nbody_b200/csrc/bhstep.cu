@@ -54,8 +54,10 @@ struct Sim {
     bool copyDeferred = false;
     // asynchronous upload (bh_upload_async): the velocities travel on a second stream while the step's tree stages and walk run
     cudaStream_t upStream = nullptr;
-    cudaEvent_t evPosReady = nullptr, evVelReady = nullptr, evPosArrived = nullptr;
+    cudaEvent_t evPosReady = nullptr, evVelReady = nullptr, evPosArrived = nullptr, evStateFree = nullptr, evPosPacked = nullptr;
     bool velPending = false;
+    bool stagingBusy = false;       // an asynchronous upload's pack kernels may still be reading the staging buffer
+    bool stagingSharedUse = false;  // the simulation's stream has used the staging buffer (bh_read ...) since the last upload
     int cur = 0;           // buffers holding the current body state
     int treePhase = 0;     // buffers the tree (child[]) was built from
     bool havePerm = false;   // a sort has run since the upload
@@ -112,6 +114,11 @@ void dropGraphs(Sim *s) {
 }
 
 int ensureStaging(Sim *s, size_t bytes) {
+    if (s->stagingBusy) {  // an asynchronous upload's pack kernels may still be reading it
+        BH_CUDA(s, cudaStreamWaitEvent(s->stream, s->evPosPacked, 0));
+        s->stagingBusy = false;
+    }
+    s->stagingSharedUse = true;
     if (bytes <= s->stagingBytes) return BH_OK;
     if (s->staging) cudaFree(s->staging);
     s->staging = nullptr;
@@ -599,6 +606,8 @@ void bh_destroy(bh_sim *sim) {
     if (s->evPosReady) cudaEventDestroy(s->evPosReady);
     if (s->evVelReady) cudaEventDestroy(s->evVelReady);
     if (s->evPosArrived) cudaEventDestroy(s->evPosArrived);
+    if (s->evStateFree) cudaEventDestroy(s->evStateFree);
+    if (s->evPosPacked) cudaEventDestroy(s->evPosPacked);
     if (s->upStream) cudaStreamDestroy(s->upStream);
     if (s->ownStream) cudaStreamDestroy(s->ownStream);
     delete s;
@@ -675,52 +684,86 @@ int bh_set_vertex_buffers(bh_sim *sim, void *pos4_device, void *vel4_device) {
     return BH_OK;
 }
 
-// deferVel: the velocities are copied and packed on a second stream; the call returns without waiting for anything
-static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bool deferVel) {
+// async: every host -> device copy runs on a second stream, so that a caller that does not wait between steps
+// (bh_step_async) gets the NEXT step's inputs across the link while the current step computes; the simulation's own
+// stream only waits for the positions (before pack_pos) and, in the finish pass, for the velocities.  Order on the
+// upload stream: [staging free] copy positions+masses -> evPosArrived -> copy velocities -> [state free] pack_vel
+// -> evVelReady.  The call returns without waiting for anything.
+static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bool async) {
     for (int i = 0; i < 7; ++i)
         if (!src[i]) return fail(s, BH_ERR_ARG, "NULL input array %d", i);
-    int rc = settleVel(s);  // a previous asynchronous upload still owns the staging buffer
-    if (rc) return rc;
+    int rc = BH_OK;
     const size_t n = s->n;
     const int grid = (s->n + 255) / 256;
     const float *dev[7];
     static const int order[7] = {0, 1, 2, 6, 3, 4, 5};  // positions and masses first
-    if (kind == cudaMemcpyHostToDevice) {
-        rc = ensureStaging(s, sizeof(float) * 7 * n);
+    if (kind != cudaMemcpyHostToDevice) async = false;
+    if (!async) {
+        rc = settleVel(s);  // a previous asynchronous upload still owns the staging buffer
         if (rc) return rc;
-        float *stg = static_cast<float *>(s->staging);
-        if (deferVel && !s->upStream) {
+    }
+    if (kind == cudaMemcpyHostToDevice) {
+        if (async && !s->upStream) {
             BH_CUDA(s, cudaStreamCreateWithFlags(&s->upStream, cudaStreamNonBlocking));
             BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosReady, cudaEventDisableTiming));
             BH_CUDA(s, cudaEventCreateWithFlags(&s->evVelReady, cudaEventDisableTiming));
+            BH_CUDA(s, cudaEventCreateWithFlags(&s->evStateFree, cudaEventDisableTiming));
+            BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosPacked, cudaEventDisableTiming));
         }
         if (!s->evPosArrived) BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosArrived, cudaEventDisableTiming));
+        if (s->stagingBytes < sizeof(float) * 7 * n) {  // (re)allocating the staging buffer: nothing may be using it
+            BH_CUDA(s, cudaStreamSynchronize(s->stream));
+            if (s->upStream) BH_CUDA(s, cudaStreamSynchronize(s->upStream));
+            rc = ensureStaging(s, sizeof(float) * 7 * n);
+            if (rc) return rc;
+            s->stagingBusy = false;
+        }
+        float *stg = static_cast<float *>(s->staging);
+        cudaStream_t up = async ? s->upStream : s->stream;
+        if (async) {
+            // the staging buffer is free once the previous upload's pack kernels have read it; other users of the
+            // staging buffer (bh_read ...) run on the simulation's stream: everything enqueued there so far comes first
+            // only as far as the STATE is concerned (evStateFree, awaited before pack_vel), not for the copies
+            if (s->stagingBusy) BH_CUDA(s, cudaStreamWaitEvent(up, s->evPosPacked, 0));
+            if (s->stagingSharedUse) {  // a bh_read / dump used the staging buffer since: order the copies behind it
+                BH_CUDA(s, cudaEventRecord(s->evStateFree, s->stream));
+                BH_CUDA(s, cudaStreamWaitEvent(up, s->evStateFree, 0));
+                s->stagingSharedUse = false;
+            }
+        }
         for (int k = 0; k < 7; ++k) {
             const int i = order[k];
-            cudaStream_t st = (deferVel && k >= 4) ? s->upStream : s->stream;
-            BH_CUDA(s, cudaMemcpyAsync(stg + i * n, src[i], sizeof(float) * n, cudaMemcpyHostToDevice, st));
+            BH_CUDA(s, cudaMemcpyAsync(stg + i * n, src[i], sizeof(float) * n, cudaMemcpyHostToDevice, up));
             dev[i] = stg + i * n;
             if (k == 3) {
-                // the position copies gate the next step: the velocity copies (second stream) and a pending vertex
-                // read-back (third stream) start behind them instead of sharing the link with them
-                BH_CUDA(s, cudaEventRecord(s->evPosArrived, s->stream));
-                if (deferVel) BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evPosArrived, 0));
+                // the position copies gate the next step: a pending vertex read-back (third stream) starts behind them
+                BH_CUDA(s, cudaEventRecord(s->evPosArrived, up));
                 rc = flushCopy(s, s->evPosArrived);
                 if (rc) return rc;
             }
         }
+        if (async) BH_CUDA(s, cudaStreamWaitEvent(s->stream, s->evPosArrived, 0));
     } else {
         for (int i = 0; i < 7; ++i) dev[i] = src[i];
-        deferVel = false;
+    }
+    if (async) {  // pack_vel overwrites the state: everything enqueued on the simulation's stream so far reads the old one
+        rc = settleVel(s);
+        if (rc) return rc;
+        BH_CUDA(s, cudaEventRecord(s->evStateFree, s->stream));
+        BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evStateFree, 0));
     }
     rc = resetState(s);
     if (rc) return rc;
     bh::pack_pos_kernel<<<grid, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[6], s->body4[0], s->velacc[0], s->perm, s->n);
     BH_CUDA(s, cudaGetLastError());
-    bh::pack_vel_kernel<<<grid, 256, 0, deferVel ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], s->n);
+    bh::pack_vel_kernel<<<grid, 256, 0, async ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], s->n);
     BH_CUDA(s, cudaGetLastError());
-    if (deferVel) {
+    if (async) {
+        BH_CUDA(s, cudaEventRecord(s->evPosPacked, s->stream));
+        BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evPosPacked, 0));  // the staging buffer is free when BOTH packs are done
         BH_CUDA(s, cudaEventRecord(s->evVelReady, s->upStream));
+        BH_CUDA(s, cudaEventRecord(s->evPosPacked, s->upStream));
+        s->stagingBusy = true;
         s->velPending = true;
         return BH_OK;
     }
@@ -1225,7 +1268,7 @@ int bh_write_universe_file(bh_sim *sim, const char *path) {
     return BH_OK;
 }
 
-int bh_measure_fp32_peak(int32_t device, double *tflops) {
+static int measurePeak(int32_t device, int packed, double *tflops) {
     if (!tflops) return BH_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, BH_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     cudaDeviceProp prop;
@@ -1239,12 +1282,13 @@ int bh_measure_fp32_peak(int32_t device, double *tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(a);
-        bh::fp32_peak_kernel<<<grid, 256>>>(out, iters, 1.0000001f, 1e-9f);
+        if (packed) bh::fp32x2_peak_kernel<<<grid, 256>>>(out, iters, 1.0000001f, 1e-9f);
+        else bh::fp32_peak_kernel<<<grid, 256>>>(out, iters, 1.0000001f, 1e-9f);
         cudaEventRecord(b);
         if (cudaEventSynchronize(b) != cudaSuccess) break;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
-        const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+        const double flops = (packed ? 4.0 : 2.0) * 64.0 * iters * 256.0 * grid;
         if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(a);
@@ -1253,5 +1297,8 @@ int bh_measure_fp32_peak(int32_t device, double *tflops) {
     *tflops = best;
     return best > 0.0 ? BH_OK : BH_ERR_CUDA;
 }
+
+int bh_measure_fp32_peak(int32_t device, double *tflops) { return measurePeak(device, 0, tflops); }
+int bh_measure_fp32x2_rate(int32_t device, double *tflops) { return measurePeak(device, 1, tflops); }
 
 }  // extern "C"

@@ -236,6 +236,9 @@ int32_t bh_abi_version(void);
 /* Measurement utility (no reference counterpart): sustained FP32 FMA rate of `device`
  * in TFLOP/s, the roofline denominator bench.py uses for the force kernel. */
 int bh_measure_fp32_peak(int32_t device, double *tflops);
+/* The same for packed FFMA2 instructions with three distinct register-pair operands (the walk's instruction): what the
+ * register file lets the fp32 pipe sustain without constant / immediate operands.  Reported beside the roofline, not used as its peak. */
+int bh_measure_fp32x2_rate(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }

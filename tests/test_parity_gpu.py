@@ -250,6 +250,38 @@ def test_async_upload_equals_upload():
     sim.close()
 
 
+def test_pipelined_host_loop():
+    """bench.py's e2e loop: upload_async / step_async / copy_vertices_async with no wait between iterations (the next
+    inputs cross the link while the current step computes); every iteration's vertices are those of a plain
+    upload + step + copy_vertices of that iteration's input."""
+    import torch
+    n = 150_000
+    universes = [gen(U.PlummerUniverseGenerator(40 + i), n) for i in range(3)]
+    want = []
+    ref = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+    ref.init(None)
+    for a in universes:
+        ref.upload(*a); ref.step(1)
+        p, v = ref.copyVertices()
+        want.append((p.copy(), v.copy()))
+    ref.close()
+    sim = GPUBarnesHutNBodySimulation(Mode.DEFAULT, n, None)
+    sim.init(None)
+    lib = sim._lib
+    pinned = [[torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in a] for a in universes]
+    outs = [(torch.empty((n, 4), dtype=torch.float32).pin_memory(), torch.empty((n, 4), dtype=torch.float32).pin_memory()) for _ in universes]
+    for rounds in range(2):
+        for a, (p4, v4) in zip(pinned, outs):
+            sim._check(lib.bh_upload_async(sim.handle, *(t.data_ptr() for t in a)))
+            sim._check(lib.bh_step_async(sim.handle, 1))
+            sim._check(lib.bh_copy_vertices_async(sim.handle, p4.data_ptr(), v4.data_ptr()))
+        sim._check(lib.bh_wait_copies(sim.handle))
+        sim._check(lib.bh_check(sim.handle))
+        for (p4, v4), (wp, wv) in zip(outs, want):
+            assert np.array_equal(p4.numpy(), wp) and np.array_equal(v4.numpy(), wv)
+    sim.close()
+
+
 def test_native_universe_writer(tmp_path):
     """bh_write_universe_file == UniverseSerializer.serialize of the current state: readable by the Python reader
     (same wire format as the reference's files, test_host.py) and by the native loader; a restart from the dump
