@@ -412,6 +412,8 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = computed, "computed 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 CUDA-core peak is not in MEASURED_PEAKS.json)"
         if lib.bh_measure_fp32_peak(local_rank, C.byref(meas)) == 0 and meas.value > 0:
             peak, peak_src = meas.value, "measured FFMA microbenchmark, this run (bh_measure_fp32_peak; MEASURED_PEAKS.json has no FP32 CUDA-core figure)"
+        x2 = C.c_double()
+        x2_rate = x2.value if lib.bh_measure_fp32x2_rate(local_rank, C.byref(x2)) == 0 else None
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -437,6 +439,7 @@ def run_ours(args, rank, world, local_rank):
         line["roofline"] = {"kernel": "walk_kernel<false>", "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak, "traffic": traffic.get("walk_kernel"), "peak_source": peak_src,
                             "peak_computed_tflops": computed, "frac_of_computed_peak": achieved / computed,
+                            "ffma2_three_register_operands_measured_tflops": x2_rate,
                             "flops_per_launch": flops, "interactions_per_body": inter / n, "opens_per_body": opens / n,
                             "ms_per_launch": f_ms, "share_of_step": f_ms / sum(stage_ms.values()),
                             "instruction_mix_ceiling": "13 fp32-pipe lane-ops + 1 MUFU per 20 counted flops: at most 0.77 of the FMA peak"}

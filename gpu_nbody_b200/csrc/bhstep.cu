@@ -8,7 +8,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -54,7 +53,7 @@ struct Sim {
     bool copyDeferred = false;
     // asynchronous upload (bh_upload_async): the velocities travel on a second stream while the step's tree stages and walk run
     cudaStream_t upStream = nullptr;
-    cudaEvent_t evPosReady = nullptr, evVelReady = nullptr, evPosArrived = nullptr, evStateFree = nullptr, evPosPacked = nullptr;
+    cudaEvent_t evVelReady = nullptr, evPosArrived = nullptr, evStateFree = nullptr, evPosPacked = nullptr;
     bool velPending = false;
     bool stagingBusy = false;       // an asynchronous upload's pack kernels may still be reading the staging buffer
     bool stagingSharedUse = false;  // the simulation's stream has used the staging buffer (bh_read ...) since the last upload
@@ -540,8 +539,6 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     // twice the resident CTAs: shorter runs per lane and a second wave that evens out the lanes' very unequal run times
     // (measured at 10^7 bodies: 1x 1.34 ms, 2x 1.14 ms, 4x 1.16 ms, 8x 1.40 ms; summarise gains 7 % from the finer cell order)
     s->buildGrid = (int)std::min<size_t>((n + bh::kBuildThreads - 1) / bh::kBuildThreads, (size_t)s->numSMs * std::max(perSM, 1) * 2);
-    if (const char *mult = getenv("BH_BUILD_GRID_MULT"))  // tuning experiment: scale the number of insertion lanes
-        s->buildGrid = std::max(1, (int)std::min<double>((double)(n + bh::kBuildThreads - 1) / bh::kBuildThreads, s->buildGrid * atof(mult)));
     s->summGrid = (int)std::min<size_t>((nc + bh::kSummThreads - 1) / bh::kSummThreads, (size_t)s->numSMs * 64);  // never waits: any grid
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bh::sort_kernel, bh::kSortThreads, 0);
     s->sortGrid = s->numSMs * std::max(perSM, 1);
@@ -603,7 +600,6 @@ void bh_destroy(bh_sim *sim) {
     if (s->evExported) cudaEventDestroy(s->evExported);
     if (s->evCopied) cudaEventDestroy(s->evCopied);
     if (s->copyStream) cudaStreamDestroy(s->copyStream);
-    if (s->evPosReady) cudaEventDestroy(s->evPosReady);
     if (s->evVelReady) cudaEventDestroy(s->evVelReady);
     if (s->evPosArrived) cudaEventDestroy(s->evPosArrived);
     if (s->evStateFree) cudaEventDestroy(s->evStateFree);
@@ -705,7 +701,6 @@ static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bo
     if (kind == cudaMemcpyHostToDevice) {
         if (async && !s->upStream) {
             BH_CUDA(s, cudaStreamCreateWithFlags(&s->upStream, cudaStreamNonBlocking));
-            BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosReady, cudaEventDisableTiming));
             BH_CUDA(s, cudaEventCreateWithFlags(&s->evVelReady, cudaEventDisableTiming));
             BH_CUDA(s, cudaEventCreateWithFlags(&s->evStateFree, cudaEventDisableTiming));
             BH_CUDA(s, cudaEventCreateWithFlags(&s->evPosPacked, cudaEventDisableTiming));
