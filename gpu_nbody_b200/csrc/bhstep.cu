@@ -59,6 +59,7 @@ struct Sim {
     bool stagingSharedUse = false;  // the simulation's stream has used the staging buffer (bh_read ...) since the last upload
     int cur = 0;           // buffers holding the current body state
     int treePhase = 0;     // buffers the tree (child[]) was built from
+    unsigned stagesRun = 0;  // bit per stage that has run since the upload: a stage needs the outputs of the ones before it
     bool havePerm = false;   // a sort has run since the upload
     bool permValid = false;  // perm[] refers to slots of the current buffers (false: bodies already lie in tree order)
     // launch geometry
@@ -165,6 +166,7 @@ int resetState(Sim *s) {
     BH_CUDA(s, cudaMemsetAsync(s->cell4, 0, sizeof(float4) * (size_t)s->nc, s->stream));
     s->cur = 0;
     s->treePhase = 0;
+    s->stagesRun = 0;
     s->havePerm = false;
     s->permValid = false;
     return BH_OK;
@@ -237,6 +239,7 @@ int launchFinish(Sim *s, bool apply) {
     if (permute) {
         s->cur = out;
         s->permValid = false;  // the bodies now lie in tree order
+        s->stagesRun &= ~(1u << BH_STAGE_BUILD);  // ... and child[] names them by their old slots: no summarise / sort without a rebuild
     }
     return BH_OK;
 }
@@ -258,6 +261,18 @@ int launchSort(Sim *s) {
 // applies them (one pass over the bodies); as single stages each completes its own reference semantics.
 int launchStage(Sim *s, int stage, bool fused) {
     const int n = s->n, m = s->m;
+    // The reference would run any kernel on whatever its buffers hold; here the tree buffers are uninitialised device
+    // memory until the stages before have run since the upload, and the tree names bodies by slots that a reordering
+    // finish pass changes, so calls that would read such state are refused.  (A force walk over a stale but complete
+    // tree is allowed, as in the reference: it reads the cells' walk records only.)
+    constexpr unsigned B = 1u << BH_STAGE_BBOX, T = 1u << BH_STAGE_BUILD, U = 1u << BH_STAGE_SUMMARIZE, O = 1u << BH_STAGE_SORT;
+    static const unsigned needs[BH_NUM_STAGES] = {0u, B, T, T | U, U | O, 0u};
+    static const char *const names[BH_NUM_STAGES] = {"bounding_box", "build_tree", "summarize", "sort", "calculate_force", "integrate"};
+    if (stage >= 0 && stage < BH_NUM_STAGES && (s->stagesRun & needs[stage]) != needs[stage])
+        return fail(s, BH_ERR_ARG, "%s called before the stages it depends on have run (since the upload / the last reordering)", names[stage]);
+    if (stage == BH_STAGE_BBOX) s->stagesRun &= ~(T | U | O);  // the root is reset: the tree is being rebuilt
+    if (stage == BH_STAGE_BUILD) s->stagesRun &= ~(U | O);
+    if (stage >= 0 && stage < BH_NUM_STAGES) s->stagesRun |= 1u << stage;
     switch (stage) {
     case BH_STAGE_BBOX:
         bh::bbox_kernel<<<s->bboxGrid, bh::kBboxThreads, 0, s->stream>>>(s->body4[s->cur], s->cell4, s->child, s->start, s->count,
@@ -365,6 +380,7 @@ int graphStep(Sim *s) {
         cudaGraph_t graph = nullptr;
         const int cur0 = s->cur, tree0 = s->treePhase;
         const bool have0 = s->havePerm, valid0 = s->permValid;
+        const unsigned stages0 = s->stagesRun;
         int64_t launches0[BH_NUM_STAGES];
         memcpy(launches0, s->stageLaunches, sizeof launches0);
         if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -375,7 +391,7 @@ int graphStep(Sim *s) {
         const int rc = launchStep(s, nullptr);
         const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
         // the capture did not run anything: restore the host-side state
-        s->cur = cur0; s->treePhase = tree0; s->havePerm = have0; s->permValid = valid0;
+        s->cur = cur0; s->treePhase = tree0; s->havePerm = have0; s->permValid = valid0; s->stagesRun = stages0;
         memcpy(s->stageLaunches, launches0, sizeof launches0);
         if (rc != BH_OK || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
@@ -394,6 +410,7 @@ int graphStep(Sim *s) {
     }
     BH_CUDA(s, cudaGraphLaunch(s->graphExec[parity], s->stream));
     // host-side mirror of what the replayed launches did
+    s->stagesRun = ((1u << BH_NUM_STAGES) - 1u) & ~(willPermute ? (1u << BH_STAGE_BUILD) : 0u);
     s->treePhase = parity;
     s->havePerm = true;
     if (willPermute) { s->cur = parity ^ 1; s->permValid = false; } else { s->permValid = true; }
@@ -825,6 +842,7 @@ int bh_calculate_force_slice(bh_sim *sim, int32_t first, int32_t count) {
     BH_ENTER(sim);
     if (!validSlice(s, first, count)) return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
     if (count == 0) return BH_OK;
+    if ((s->stagesRun & (1u << BH_STAGE_SORT)) == 0) return fail(s, BH_ERR_ARG, "calculate_force called before the tree stages have run since the upload");
     launchWalk(s, first, count, false);
     BH_CUDA(s, cudaGetLastError());
     s->stageLaunches[BH_STAGE_FORCE] += 1;
@@ -836,6 +854,7 @@ int bh_calculate_force_slice_p2p(bh_sim *sim, int32_t first, int32_t count) {
     if (!s->p2p) return fail(s, BH_ERR_ARG, "bh_ipc_set_peers has not been called");
     if (!validSlice(s, first, count)) return fail(s, BH_ERR_ARG, "bad slice [%d, %d): first must be a multiple of vote_width", first, first + count);
     if (count == 0) return BH_OK;
+    if ((s->stagesRun & (1u << BH_STAGE_SORT)) == 0) return fail(s, BH_ERR_ARG, "calculate_force called before the tree stages have run since the upload");
     launchWalk(s, first, count, true);
     BH_CUDA(s, cudaGetLastError());
     s->stageLaunches[BH_STAGE_FORCE] += 1;

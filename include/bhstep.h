@@ -131,7 +131,11 @@ int bh_upload_device(bh_sim *sim, const float *x, const float *y, const float *z
                      const float *vz, const float *mass);
 
 /* The per-stage kernel contract, one call per executeSimulationKernel (GPUBH:258-263,273-275).
- * Each enqueues on the simulation's stream and waits for it, like finish() at GPUBH:275. */
+ * Each enqueues on the simulation's stream and waits for it, like finish() at GPUBH:275.
+ * A stage whose inputs do not exist yet is refused with BH_ERR_ARG instead of reading uninitialised device memory:
+ * build_tree needs bounding_box, summarize needs build_tree, sort needs build_tree + summarize, calculate_force needs
+ * summarize + sort (each since the last upload); a calculate_force over the previous step's tree is allowed, as in the
+ * reference, but summarize / sort are not once a step has physically reordered the bodies (the tree names them by slot). */
 int bh_bounding_box(bh_sim *sim);    /* kernels/nbody/boundingbox.cl:21     */
 int bh_build_tree(bh_sim *sim);      /* kernels/nbody/buildtree.cl:13       */
 int bh_summarize(bh_sim *sim);       /* kernels/nbody/summarizetree.cl:16   */

@@ -522,6 +522,19 @@ def test_argument_errors_and_async_api():
     assert lib.bh_read(sim.handle, 0, buf.ctypes.data, 10 ** 9) == -2
     assert lib.bh_calculate_force_slice(sim.handle, 8, 16) == -2                   # not a multiple of the vote width
     assert b"vote_width" in lib.bh_last_error(sim.handle)
+    # stages out of order are refused (the tree buffers are not initialised until the stages before have run)
+    fresh, _ = parity.make_pair(a, counting=False)
+    for call in (lib.bh_build_tree, lib.bh_summarize, lib.bh_sort, lib.bh_calculate_force):
+        assert call(fresh.handle) == -2 and b"before the stages" in lib.bh_last_error(fresh.handle)
+    assert lib.bh_calculate_force_slice(fresh.handle, 0, 16) == -2
+    assert lib.bh_bounding_box(fresh.handle) == 0 and lib.bh_summarize(fresh.handle) == -2 and lib.bh_build_tree(fresh.handle) == 0
+    assert lib.bh_integrate(fresh.handle) == 0   # integrate needs nothing (integrate.cl only reads pos / vel / acc)
+    fresh.upload(*a)
+    assert lib.bh_build_tree(fresh.handle) == -2   # an upload starts over
+    fresh.step(1)
+    assert lib.bh_calculate_force(fresh.handle) == 0   # a stale tree is walked, as the reference would
+    assert lib.bh_sort(fresh.handle) == -2             # ... but its body ids are stale after the reordering: no sort without a rebuild
+    fresh.close()
     # async step + check == step
     ref, _ = parity.make_pair(a, counting=False)
     ref.step(2)
