@@ -7,13 +7,11 @@ cd "$(dirname "$0")/.."
 mkdir -p gpu_nbody_b200/variants
 build() {  # name batch sub trips scap ctas
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -I include \
-       -DBH_WALK_BATCH=$2 -DBH_WALK_SUB=$3 -DBH_WALK_TRIPS=$4 -DBH_WALK_SCAP=$5 -DBH_WALK_CTAS=$6 -Xptxas -v \
+       -DBH_WALK_BATCH=$2 -DBH_WALK_SUB=$3 -DBH_WALK_TRIPS=$4 -DBH_WALK_SCAP=$5 -DBH_WALK_CTAS=$6 $7 -Xptxas -v \
        -o gpu_nbody_b200/variants/$1.so gpu_nbody_b200/csrc/bhstep.cu 2>&1 | grep -A2 "walk_kernelILb0" | grep Used | sed "s/^/$1: /"
 }
-build b16s8t6c4 16 8 6 96 4 &
-build b16s8t6c5 16 8 6 96 5 &
-build b12s6t5c5 12 6 5 96 5 &
-build b20s10t8c4 20 10 8 96 4 &
 build b16s8t5c4 16 8 5 96 4 &
-build b16s8t7c4 16 8 7 96 4 &
+build b12s6t5c4 12 6 5 96 4 &
+build b20s10t7c4 20 10 7 96 4 &
+build b16s8t5c5 16 8 5 96 5 &
 wait
