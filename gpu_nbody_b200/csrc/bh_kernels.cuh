@@ -485,6 +485,12 @@ __global__ void __launch_bounds__(kSummThreads, 4) summarize_kernel(const float4
                     orow[bpos++] = c[k];
                 }
             }
+            // whole 32-byte sectors only: a partially written sector costs a DRAM read (merge) when it leaves L2
+            // (measured: 0.21 GB less DRAM read traffic, 0.996 -> 0.922 ms at 10^7 bodies)
+            if (used & 1) orow[used] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                if (k >= used && (k & 3) != 0 && (k & ~3) < used) mrow[k] = make_int2(0, 0);
             reinterpret_cast<int4 *>(row)[0] = make_int4(out[0], out[1], out[2], out[3]);
             reinterpret_cast<int4 *>(row)[1] = make_int4(out[4], out[5], out[6], out[7]);
             meta[cell - n] = ncell | ((used - ncell) << 4);  // deep walk: #child cells, #child bodies
