@@ -35,7 +35,7 @@ class BhStats(C.Structure):
                 ("max_depth", C.c_int32), ("step", C.c_int32), ("error", C.c_int32),
                 ("steps_timed", C.c_int64), ("stage_ms", C.c_double * 6), ("stage_launches", C.c_int64 * 6),
                 ("interactions", C.c_int64), ("opens", C.c_int64), ("barrier_ms", C.c_double), ("deep_walk", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("walk_spills", C.c_int32)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -60,6 +60,8 @@ struct Scalars {
     int error;
     int walkTicket;   // next chunk of eight vote groups the force walk hands to a warp (reset before every walk)
     int rootEntry;    // walk entry of the root cell (written by summarise)
+    int walkSpills;   // times a group's cell stack spilled to global memory in the last walk (diagnostic)
+    int pad0;
     unsigned long long interactions;
     unsigned long long opens;
 };
@@ -820,6 +822,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSM) walk_kernel(cons
                         if (l + 4 * t < rest) sts_s32(stkBase + 4u * (unsigned)(l + 4 * t), keep[t]);
                     spilled += kWalkSpill;
                     stkTop -= 4u * kWalkSpill;
+                    if (l == 0) atomicAdd(&sc->walkSpills, 1);
                 }
             }
             __syncwarp();

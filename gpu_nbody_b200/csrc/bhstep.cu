@@ -195,6 +195,7 @@ void launchWalk(Sim *s, int first, int cnt, bool peers, bool potential = false) 
         const int grid = std::max(1, std::min(s->walkGrid, (groups + 31) / 32));
         const size_t smem = sizeof(bh::WalkShared);
         cudaMemsetAsync(&s->sc->walkTicket, 0, sizeof(int), s->stream);
+        cudaMemsetAsync(&s->sc->walkSpills, 0, sizeof(int), s->stream);
         if (potential)
             bh::walk_kernel<false, true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         else if (s->counting)
@@ -1087,6 +1088,7 @@ int bh_stats(bh_sim *sim, bh_stats_t *out) {
     out->interactions = (int64_t)s->hostSc->interactions;
     out->opens = (int64_t)s->hostSc->opens;
     out->deep_walk = (s->vote != 16 || s->forceDeep) ? 1 : 0;
+    out->walk_spills = s->hostSc->walkSpills;
     return BH_OK;
 }
 

@@ -181,7 +181,7 @@ class GPUBarnesHutNBodySimulation(AbstractNBodySimulation):
         self._check(self._lib.bh_generate_universe(self._sim, k, int(seed), float(p0), float(p1), float(p2)))
 
     def setForceDeepWalk(self, on=True):
-        """Validation: always run the deep-tree fallback kernel of the force walk."""
+        """Validation / A-B timing: run the force stage with the shared-stack walk kernel (the one used for 32-wide votes)."""
         self._check(self._lib.bh_set_force_deep_walk(self._sim, int(on)))
 
     def setVertexBuffers(self, pos4_device_ptr, vel4_device_ptr):

@@ -82,7 +82,7 @@ typedef struct bh_stats_t {
     int64_t opens;            /* (body,cell) opening tests that pushed, same call */
     double barrier_ms;        /* summed CUDA-event time of the multi-GPU peer barrier (ABI >= 2) */
     int32_t deep_walk;        /* 1 = the force stage runs the shared-stack walk kernel (vote width 32 or bh_set_force_deep_walk) */
-    int32_t reserved;
+    int32_t walk_spills;      /* times a vote group's cell stack spilled to global memory in the last force walk (deep trees) */
 } bh_stats_t;
 
 /* GPUBH.init():111-151 -- context, node-pool sizing (219-227), buffer creation (153-181).

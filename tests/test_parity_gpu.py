@@ -341,11 +341,12 @@ def test_full_size_1m_against_the_oracle():
     st = sim.stats()
     assert 0.4 < st["cells_used"] / n < 0.6 and 10 <= st["max_depth"] <= 40
     assert 2000 < st["interactions"] / n < 4000 and st["deep_walk"] == 0
+    print("walk_spills at 2^20:", st["walk_spills"])
     sim.close()
 
 
-def test_deep_walk_fallback_kernel():
-    """The kernel that takes over when a tree is too deep for the fast walk's shared-memory stacks, forced on."""
+def test_shared_stack_walk_kernel():
+    """The second implementation of the force walk (one shared stack per warp; used for 32-wide votes), forced on for 16-wide votes."""
     a = gen(U.PlummerUniverseGenerator(9), 100_000)
     sim, orc = parity.make_pair(a)
     sim.setForceDeepWalk(True)
@@ -504,6 +505,7 @@ def test_full_size_properties_10m():
     assert err.max() <= parity.ACC_RTOL
     st = sim.stats()
     assert 3000 < st["interactions"] / n < 3600
+    assert st["walk_spills"] > 0   # a 22-level tree overflows some groups' shared-memory stacks: the spill path is part of this parity
     sim.close()
 
 
