@@ -101,7 +101,9 @@ int bh_set_theta_macro(bh_sim *sim, float theta_macro);
  * returns to it. */
 int bh_set_stream(bh_sim *sim, void *cuda_stream);
 int bh_use_private_stream(bh_sim *sim);
-/* 1 = record CUDA events around every stage (bh_stats.stage_ms); 0 = off (default). */
+/* 1 = record CUDA events around every stage (bh_stats.stage_ms; steps are then launched kernel by kernel instead of
+ * replaying the step's CUDA graph); 0 = off (default).  Events exist for 64 steps between two calls that wait for the
+ * device: bh_step splits longer runs itself, bh_step_async times the first 64 steps of a longer burst only. */
 int bh_set_profiling(bh_sim *sim, int32_t on);
 /* 1 = count interactions/opens in the next force calls (slower kernel variant); 0 = off. */
 int bh_set_counting(bh_sim *sim, int32_t on);
