@@ -51,6 +51,7 @@ constexpr int kSpinBudget = 1 << 24;  // polls before a device-side wait gives u
 constexpr int kEntryMask = 0x7ffffff;  // cell - N of a walk entry (27 bits: NC <= 2^27)
 constexpr int kCountMask = 0xfffffff;  // bodyCount of a count word (28 bits)
 
+constexpr int kNothingDirty = 0x7fffffff;
 struct Scalars {
     int step;         // init -1 (GPUBH:165)
     int blockCount;   // last-block-done ticket of bbox_kernel
@@ -61,7 +62,7 @@ struct Scalars {
     int walkTicket;   // next chunk of eight vote groups the force walk hands to a warp (reset before every walk)
     int rootEntry;    // walk entry of the root cell (written by summarise)
     int walkSpills;   // times a group's cell stack spilled to global memory in the last walk (diagnostic)
-    int pad0;
+    int lowWater;     // lowest cell a build has allocated since the last reset, kNothingDirty before the first bbox
     unsigned long long interactions;
     unsigned long long opens;
 };
@@ -178,6 +179,8 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(const float4 *__rest
         const float ry = __fmul_rn(0.5f, __fadd_rn(mny, mxy));
         const float rz = __fmul_rn(0.5f, __fadd_rn(mnz, mxz));
         sc->radius = __fmul_rn(0.5f, fmaxf(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny)), __fsub_rn(mxz, mnz)));
+        // what the next reset has to clear: the root row written here and the cells of every build so far
+        sc->lowWater = sc->lowWater == kNothingDirty ? m : min(sc->lowWater, sc->bottom);
         sc->bottom = m;
         cell4[m - n] = make_float4(rx, ry, rz, -1.0f);
         start[m - n] = 0;
@@ -1165,20 +1168,51 @@ __global__ void barrier_kernel(const PeerFlags pf, unsigned long long *seq, Scal
 // positions + masses (what the tree stages and the walk read), and velocities + the host's numbering (what only the
 // finish pass reads): two kernels so that an asynchronous upload can deliver the second half while the step already runs
 __global__ void pack_pos_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
-                                const float *__restrict__ mass, float4 *__restrict__ body4, float4 *__restrict__ velacc,
+                                const float *__restrict__ mass, float4 *__restrict__ body4, const int *__restrict__ slotOf,
                                 int *__restrict__ perm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    body4[i] = make_float4(x[i], y[i], z[i], mass[i]);
-    velacc[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int slot = slotOf ? slotOf[i] : i;
+    if ((unsigned)slot < (unsigned)n) body4[slot] = make_float4(x[i], y[i], z[i], mass[i]);
     perm[i] = 0;
 }
 
 __global__ void pack_vel_kernel(const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
-                                float4 *__restrict__ velacc, int n) {
+                                float4 *__restrict__ velacc, const int *__restrict__ slotOf, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    velacc[2 * (size_t)i] = make_float4(vx[i], vy[i], vz[i], __int_as_float(i));
+    const int slot = slotOf ? slotOf[i] : i;
+    if ((unsigned)slot >= (unsigned)n) return;
+    velacc[2 * (size_t)slot] = make_float4(vx[i], vy[i], vz[i], __int_as_float(i));  // one whole 32-byte sector per body
+    velacc[2 * (size_t)slot + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// Where an upload puts body i: the slot the body with the host's number i occupies in the state being replaced
+// (tree order of the last step).  A host that sends its bodies every step -- the same bodies, a little further on --
+// then hands the tree stages bodies that are already nearly in tree order, as in a run that never leaves the
+// device.  Any placement is correct (the host's numbering travels with the body, see origId); this one is fast.
+__global__ void slot_of_kernel(const float4 *__restrict__ velacc, int *__restrict__ slotOf, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int id = __float_as_int(velacc[2 * (size_t)s].w);
+    if ((unsigned)id < (unsigned)n) slotOf[id] = s;
+}
+
+// A reset (upload, generated universe) returns the tree buffers to the reference's initial state, all zeros
+// (GPUBH:155-179).  Only the cells builds have allocated since the last reset can differ from that.
+__global__ void clear_tree_kernel(int *__restrict__ child, int *__restrict__ start, int *__restrict__ count,
+                                  float4 *__restrict__ cell4, const Scalars *sc, int n, int m) {
+    if (sc->lowWater == kNothingDirty) return;  // no stage has run since the last reset
+    int lo = min(sc->lowWater, sc->bottom);
+    if (sc->error != 0 || lo < n) lo = n;  // a failed build: take no chances
+    const int4 zero = make_int4(0, 0, 0, 0);
+    for (long long c = lo - n + blockIdx.x * (long long)blockDim.x + threadIdx.x; c <= m - n; c += gridDim.x * (long long)blockDim.x) {
+        reinterpret_cast<int4 *>(child)[2 * c] = zero;
+        reinterpret_cast<int4 *>(child)[2 * c + 1] = zero;
+        start[c] = 0;
+        count[c] = 0;
+        cell4[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
 }
 
 // Logical float buffers (GPUBH:198-205): bodies 0..n-1 in the host's numbering, cells n..m; `which`: 0-2 pos,
@@ -1227,15 +1261,17 @@ __global__ void export_shifted_kernel(const int *__restrict__ src, long long ski
 }
 
 // child[8(M+1)]: zeros for the body rows; body slots translated to the host's numbering through the origIds of the
-// buffers the tree was built from
-__global__ void export_child_kernel(const int *__restrict__ child, const float4 *__restrict__ velaccTree, int n,
+// buffers the tree was built from.  Rows of cells no build has allocated (below `bottom`, or all of them after a
+// reset) hold the initial zeros, which are not body slots.
+__global__ void export_child_kernel(const int *__restrict__ child, const float4 *__restrict__ velaccTree, const Scalars *sc, int n,
                                     int *__restrict__ out, long long len) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= len) return;
     int v = 0;
     if (i >= 8ll * n) {
         v = child[i - 8ll * n];
-        if (v >= 0 && v < n) v = __float_as_int(velaccTree[2 * (size_t)v].w);
+        const bool allocated = sc->lowWater != kNothingDirty && (i >> 3) >= sc->bottom;
+        if (allocated && v >= 0 && v < n) v = __float_as_int(velaccTree[2 * (size_t)v].w);
     }
     out[i] = v;
 }

@@ -55,6 +55,8 @@ struct Sim {
     cudaStream_t upStream = nullptr;
     cudaEvent_t evVelReady = nullptr, evPosArrived = nullptr, evStateFree = nullptr, evPosPacked = nullptr;
     bool velPending = false;
+    bool placed = false;     // the body buffers hold a complete state: every slot has a body with a distinct host number
+    int *slotOf = nullptr;   // upload placement: slot of the body with host number i in the state being replaced
     bool stagingBusy = false;       // an asynchronous upload's pack kernels may still be reading the staging buffer
     bool stagingSharedUse = false;  // the simulation's stream has used the staging buffer (bh_read ...) since the last upload
     int cur = 0;           // buffers holding the current body state
@@ -152,18 +154,26 @@ int flushCopy(Sim *s, cudaEvent_t after) {
     return BH_OK;
 }
 
-int resetState(Sim *s) {
-    // GPUBH:155-179: everything zero except step = -1, maxDepth = 1
+int resetState(Sim *s, bool everything = false) {
+    // GPUBH:155-179: everything zero except step = -1, maxDepth = 1.  The tree buffers (1.1 GB at 10^7 bodies) are
+    // zeroed as a whole once, at creation; later resets clear the cells that builds have allocated since (the device
+    // knows which: Scalars::lowWater), a third of the buffers in a typical run.
+    if (everything) {
+        BH_CUDA(s, cudaMemsetAsync(s->child, 0, sizeof(int) * 8 * (size_t)s->nc, s->stream));
+        BH_CUDA(s, cudaMemsetAsync(s->start, 0, sizeof(int) * (size_t)s->nc, s->stream));
+        BH_CUDA(s, cudaMemsetAsync(s->count, 0, sizeof(int) * (size_t)s->nc, s->stream));
+        BH_CUDA(s, cudaMemsetAsync(s->cell4, 0, sizeof(float4) * (size_t)s->nc, s->stream));
+    } else {
+        bh::clear_tree_kernel<<<s->numSMs * 8, 256, 0, s->stream>>>(s->child, s->start, s->count, s->cell4, s->sc, s->n, s->m);
+        BH_CUDA(s, cudaGetLastError());
+    }
     bh::Scalars init;
     memset(&init, 0, sizeof init);
     init.step = -1;
     init.maxDepth = 1;
+    init.lowWater = bh::kNothingDirty;
     *s->hostSc = init;
     BH_CUDA(s, cudaMemcpyAsync(s->sc, s->hostSc, sizeof init, cudaMemcpyHostToDevice, s->stream));
-    BH_CUDA(s, cudaMemsetAsync(s->child, 0, sizeof(int) * 8 * (size_t)s->nc, s->stream));
-    BH_CUDA(s, cudaMemsetAsync(s->start, 0, sizeof(int) * (size_t)s->nc, s->stream));
-    BH_CUDA(s, cudaMemsetAsync(s->count, 0, sizeof(int) * (size_t)s->nc, s->stream));
-    BH_CUDA(s, cudaMemsetAsync(s->cell4, 0, sizeof(float4) * (size_t)s->nc, s->stream));
     s->cur = 0;
     s->treePhase = 0;
     s->stagesRun = 0;
@@ -577,7 +587,7 @@ int bh_create(bh_sim **out, int32_t nbodies, float theta, float eps2, float dt, 
     }
     cudaMemsetAsync(s->perm, 0, sizeof(int) * n, s->stream);
     cudaMemsetAsync(s->accAlloc, 0, accBytes(s) + 512, s->stream);
-    if (resetState(s) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+    if (resetState(s, true) != BH_OK || cudaStreamSynchronize(s->stream) != cudaSuccess) {
         g_createError = s->lastError.empty() ? "initial reset failed" : s->lastError;
         bh_destroy(reinterpret_cast<bh_sim *>(s));
         return BH_ERR_CUDA;
@@ -609,7 +619,7 @@ void bh_destroy(bh_sim *sim) {
     for (int b = 0; b < 2; ++b) { cudaFree(s->body4[b]); cudaFree(s->velacc[b]); }
     cudaFree(s->cell4); cudaFree(s->octet); cudaFree(s->ometa); cudaFree(s->accAlloc);
     cudaFree(s->child); cudaFree(s->start); cudaFree(s->count); cudaFree(s->perm); cudaFree(s->meta); cudaFree(s->parent); cudaFree(s->arrived);
-    cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging); cudaFree(s->spill);
+    cudaFree(s->partials); cudaFree(s->sc); cudaFree(s->staging); cudaFree(s->spill); cudaFree(s->slotOf);
     if (s->hostSc) cudaFreeHost(s->hostSc);
     if (s->evCreated)
         for (auto &row : s->ev)
@@ -759,18 +769,30 @@ static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bo
     } else {
         for (int i = 0; i < 7; ++i) dev[i] = src[i];
     }
-    if (async) {  // pack_vel overwrites the state: everything enqueued on the simulation's stream so far reads the old one
+    if (async) {  // the velocities of a previous asynchronous upload are part of the state that is read next
         rc = settleVel(s);
         if (rc) return rc;
+    }
+    // Placement: body i goes to the slot the body with the same host number has in the state being replaced (tree order
+    // of the last step), so that a host that sends its bodies every step keeps the tree stages' locality.
+    const int *slotOf = nullptr;
+    if (s->placed) {
+        if (!s->slotOf) BH_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->slotOf), sizeof(int) * n));
+        bh::slot_of_kernel<<<grid, 256, 0, s->stream>>>(s->velacc[s->cur], s->slotOf, s->n);
+        BH_CUDA(s, cudaGetLastError());
+        slotOf = s->slotOf;
+    }
+    if (async) {  // pack_vel overwrites the state: everything enqueued on the simulation's stream so far reads the old one
         BH_CUDA(s, cudaEventRecord(s->evStateFree, s->stream));
         BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evStateFree, 0));
     }
     rc = resetState(s);
     if (rc) return rc;
-    bh::pack_pos_kernel<<<grid, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[6], s->body4[0], s->velacc[0], s->perm, s->n);
+    bh::pack_pos_kernel<<<grid, 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[6], s->body4[0], slotOf, s->perm, s->n);
     BH_CUDA(s, cudaGetLastError());
-    bh::pack_vel_kernel<<<grid, 256, 0, async ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], s->n);
+    bh::pack_vel_kernel<<<grid, 256, 0, async ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], slotOf, s->n);
     BH_CUDA(s, cudaGetLastError());
+    s->placed = true;
     if (async) {
         BH_CUDA(s, cudaEventRecord(s->evPosPacked, s->stream));
         BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evPosPacked, 0));  // the staging buffer is free when BOTH packs are done
@@ -1002,7 +1024,7 @@ int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
         bh::export_shifted_kernel<<<grid, 256, 0, s->stream>>>(s->start, s->n, -1, iout, count);
         break;
     case BH_CHILD:
-        bh::export_child_kernel<<<grid, 256, 0, s->stream>>>(s->child, s->velacc[s->treePhase], s->n, iout, count);
+        bh::export_child_kernel<<<grid, 256, 0, s->stream>>>(s->child, s->velacc[s->treePhase], s->sc, s->n, iout, count);
         break;
     case BH_SORTED:
         if (!s->havePerm) BH_CUDA(s, cudaMemsetAsync(iout, 0, 4 * (size_t)count, s->stream));  // GPUBH:178: zeros until the first sort
@@ -1110,6 +1132,7 @@ int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, flo
     bh::generate_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[0], s->velacc[0], s->perm, s->n, kind, seed, p0, p1, p2);
     BH_CUDA(s, cudaGetLastError());
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->placed = true;
     return BH_OK;
 }
 

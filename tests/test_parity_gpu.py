@@ -408,6 +408,43 @@ def test_physical_order_is_invisible():
         assert np.array_equal(outs[0][k].view(np.uint32), outs[1][k].view(np.uint32)), k
 
 
+def test_reupload_keeps_tree_order_and_resets_the_tree_buffers():
+    """An upload over a stepped state stores body i in the slot of the old body i (tree order of the last step: the
+    tree stages keep their locality when the host sends the bodies every step) and clears the cells builds have used
+    since the last reset.  Neither is visible: the buffers are those of a freshly created simulation, stage by stage
+    against the oracle and bitwise against a fresh simulation after further steps."""
+    n = 60_000
+    a = gen(U.PlummerUniverseGenerator(77), n)
+    sim, _ = parity.make_pair(a)
+    sim.step(3)
+    moved = [sim.readBuffer(k, n).copy() for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "mass")]
+    b = gen(U.TwoDiskGalaxiesGenerator(8, 9), n)   # an unrelated universe goes through the same placement
+    for arrays in (moved, b, a):
+        sim.upload(*arrays)
+        for k, w in zip(("posX", "posY", "posZ", "velX", "velY", "velZ", "mass"), arrays):   # host numbering, as uploaded
+            assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), np.asarray(w, dtype=np.float32).view(np.uint32)), k
+        for k in ("child", "start", "bodyCount", "sorted", "accX"):   # GPUBH:155-179: everything zero after a reset
+            assert not sim.readBuffer(k).any(), k
+        for k in ("posX", "posY", "posZ", "mass"):                  # ... cells included
+            assert not sim.readBuffer(k)[n:].any(), k
+        assert sim.scalar("step") == -1 and sim.scalar("bottom") == 0 and sim.scalar("maxDepth") == 1
+        fresh, orc = parity.make_pair(arrays)
+        parity.check_full_step(sim, orc)       # every stage against the oracle, on the re-uploaded simulation
+        fresh.step(1)
+        sim.step(2); fresh.step(2)
+        for k in ("posX", "posY", "posZ", "velX", "velY", "velZ", "accX", "accY", "accZ", "sorted"):   # (cell numbers are a race)
+            assert np.array_equal(sim.readBuffer(k, n).view(np.uint32), fresh.readBuffer(k, n).view(np.uint32)), k
+        assert not sim.readBuffer("child")[: 8 * (n + n // 4)].any()   # rows no build has ever allocated stay zero
+        fresh.close()
+    # a diagnostic tree (tree stages without a step) on a fresh upload also dirties cells that the next reset must clear
+    sim.upload(*a)
+    sim.diagnostics(2)
+    sim.upload(*b)
+    for k in ("child", "start", "bodyCount"):
+        assert not sim.readBuffer(k).any(), k
+    sim.close()
+
+
 def test_device_diagnostics_match_host_energy():
     """bh_diagnostics (printEnergy / printImpulse on the device) against the oracle's double-precision O(N^2) sum."""
     import oracle
