@@ -1301,6 +1301,25 @@ __global__ void copy_vertices_kernel(const float4 *__restrict__ body4, const flo
     if (vel) vel[id] = make_float4(v.x, v.y, v.z, 1.0f);
 }
 
+// The same by gather: vertex i comes from the slot of body i.  Whole 16-byte vertices are written in order; the
+// scattered side is the reads (a 32-byte sector per 16 bytes used), which cost a third of what scattered 16-byte
+// writes do (each of those makes L2 fetch the rest of its sector from DRAM first).
+__global__ void copy_vertices_gather_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc,
+                                            const int *__restrict__ slotOf, float4 *__restrict__ pos, float4 *__restrict__ vel, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = slotOf[i];
+    if ((unsigned)slot >= (unsigned)n) return;
+    if (pos) {
+        const float4 p = body4[slot];
+        pos[i] = make_float4(p.x, p.y, p.z, 1.0f);
+    }
+    if (vel) {
+        const float4 v = velacc[2 * (size_t)slot];
+        vel[i] = make_float4(v.x, v.y, v.z, 1.0f);
+    }
+}
+
 // SoA state dump in the host's numbering (bh_write_universe_file): out = 7 arrays of n floats
 __global__ void export_universe_kernel(const float4 *__restrict__ body4, const float4 *__restrict__ velacc, float *__restrict__ out,
                                        int n) {
@@ -1442,6 +1461,25 @@ __global__ void __launch_bounds__(256) tree_potential_kernel(const float4 *__res
 }
 
 __global__ void adjust_step_kernel(Scalars *sc, int delta) { sc->step += delta; }
+
+// Small device-side resets as kernels, not cudaMemsetAsync / cudaMemcpyAsync: those may be queued on a copy engine,
+// where they wait behind a bulk host transfer of the asynchronous boundary (measured: ~0.9 ms per step while a
+// 320 MB read-back was in flight).
+__global__ void reset_walk_kernel(Scalars *sc) {
+    sc->walkTicket = 0;
+    sc->walkSpills = 0;
+}
+__global__ void reset_counters_kernel(Scalars *sc) {
+    sc->interactions = 0;
+    sc->opens = 0;
+}
+__global__ void init_scalars_kernel(Scalars *sc) {  // GPUBH:155-179: everything zero except step = -1, maxDepth = 1
+    Scalars init = {};
+    init.step = -1;
+    init.maxDepth = 1;
+    init.lowWater = kNothingDirty;
+    *sc = init;
+}
 
 // ---- measurement utility: FP32 FMA peak of the device (roofline denominator of the force kernel) ----
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {

@@ -56,7 +56,8 @@ struct Sim {
     cudaEvent_t evVelReady = nullptr, evPosArrived = nullptr, evStateFree = nullptr, evPosPacked = nullptr;
     bool velPending = false;
     bool placed = false;     // the body buffers hold a complete state: every slot has a body with a distinct host number
-    int *slotOf = nullptr;   // upload placement: slot of the body with host number i in the state being replaced
+    int *slotOf = nullptr;   // slot of the body with host number i (upload placement, vertex export by gather)
+    bool slotOfValid = false;  // ... for the current state (any pass that moves bodies invalidates it)
     bool stagingBusy = false;       // an asynchronous upload's pack kernels may still be reading the staging buffer
     bool stagingSharedUse = false;  // the simulation's stream has used the staging buffer (bh_read ...) since the last upload
     int cur = 0;           // buffers holding the current body state
@@ -139,6 +140,30 @@ int settleVel(Sim *s) {
     return BH_OK;
 }
 
+// slotOf[] for the current state (the caller has settled the velocities: the host numbers live beside them)
+int ensureSlotOf(Sim *s) {
+    if (!s->slotOf) BH_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->slotOf), sizeof(int) * (size_t)s->n));
+    if (!s->slotOfValid) {
+        bh::slot_of_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->velacc[s->cur], s->slotOf, s->n);
+        BH_CUDA(s, cudaGetLastError());
+        s->slotOfValid = true;
+    }
+    return BH_OK;
+}
+
+// copyvertices.cl on the current state, host numbering, to device memory
+int exportVertices(Sim *s, float4 *pos, float4 *vel) {
+    if (!s->placed) {  // nothing has been uploaded or generated yet: slot order (all host numbers are zero)
+        bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], pos, vel, s->n);
+    } else {
+        int rc = ensureSlotOf(s);
+        if (rc) return rc;
+        bh::copy_vertices_gather_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], s->slotOf, pos, vel, s->n);
+    }
+    BH_CUDA(s, cudaGetLastError());
+    return BH_OK;
+}
+
 // bh_copy_vertices_async exports at once but enqueues its device -> host copies lazily: if an upload follows, they start
 // behind that upload's position copies (which gate the next step) instead of competing with them for the link
 int flushCopy(Sim *s, cudaEvent_t after) {
@@ -167,13 +192,8 @@ int resetState(Sim *s, bool everything = false) {
         bh::clear_tree_kernel<<<s->numSMs * 8, 256, 0, s->stream>>>(s->child, s->start, s->count, s->cell4, s->sc, s->n, s->m);
         BH_CUDA(s, cudaGetLastError());
     }
-    bh::Scalars init;
-    memset(&init, 0, sizeof init);
-    init.step = -1;
-    init.maxDepth = 1;
-    init.lowWater = bh::kNothingDirty;
-    *s->hostSc = init;
-    BH_CUDA(s, cudaMemcpyAsync(s->sc, s->hostSc, sizeof init, cudaMemcpyHostToDevice, s->stream));
+    bh::init_scalars_kernel<<<1, 1, 0, s->stream>>>(s->sc);
+    BH_CUDA(s, cudaGetLastError());
     s->cur = 0;
     s->treePhase = 0;
     s->stagesRun = 0;
@@ -204,8 +224,7 @@ void launchWalk(Sim *s, int first, int cnt, bool peers, bool potential = false) 
         const int groups = (cnt + 15) / 16;
         const int grid = std::max(1, std::min(s->walkGrid, (groups + 31) / 32));
         const size_t smem = sizeof(bh::WalkShared);
-        cudaMemsetAsync(&s->sc->walkTicket, 0, sizeof(int), s->stream);
-        cudaMemsetAsync(&s->sc->walkSpills, 0, sizeof(int), s->stream);
+        bh::reset_walk_kernel<<<1, 1, 0, s->stream>>>(s->sc);
         if (potential)
             bh::walk_kernel<false, true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         else if (s->counting)
@@ -249,6 +268,7 @@ int launchFinish(Sim *s, bool apply) {
     BH_CUDA(s, cudaGetLastError());
     if (permute) {
         s->cur = out;
+        s->slotOfValid = false;
         s->permValid = false;  // the bodies now lie in tree order
         s->stagesRun &= ~(1u << BH_STAGE_BUILD);  // ... and child[] names them by their old slots: no summarise / sort without a rebuild
     }
@@ -305,7 +325,7 @@ int launchStage(Sim *s, int stage, bool fused) {
         break;
     }
     case BH_STAGE_FORCE: {
-        if (s->counting) BH_CUDA(s, cudaMemsetAsync(&s->sc->interactions, 0, 2 * sizeof(unsigned long long), s->stream));
+        if (s->counting) bh::reset_counters_kernel<<<1, 1, 0, s->stream>>>(s->sc);
         const bool sliced = fused && s->p2p;
         launchWalk(s, sliced ? s->sliceFirst : 0, sliced ? s->sliceCount : n, sliced);
         if (!fused) {
@@ -424,7 +444,7 @@ int graphStep(Sim *s) {
     s->stagesRun = ((1u << BH_NUM_STAGES) - 1u) & ~(willPermute ? (1u << BH_STAGE_BUILD) : 0u);
     s->treePhase = parity;
     s->havePerm = true;
-    if (willPermute) { s->cur = parity ^ 1; s->permValid = false; } else { s->permValid = true; }
+    if (willPermute) { s->cur = parity ^ 1; s->permValid = false; s->slotOfValid = false; } else { s->permValid = true; }
     for (int st = 0; st < BH_NUM_STAGES; ++st) s->stageLaunches[st] += 1;
     if (s->p2p) s->stageLaunches[BH_STAGE_FORCE]++;  // the peer barrier
     return BH_OK;
@@ -777,10 +797,9 @@ static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bo
     // of the last step), so that a host that sends its bodies every step keeps the tree stages' locality.
     const int *slotOf = nullptr;
     if (s->placed) {
-        if (!s->slotOf) BH_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->slotOf), sizeof(int) * n));
-        bh::slot_of_kernel<<<grid, 256, 0, s->stream>>>(s->velacc[s->cur], s->slotOf, s->n);
-        BH_CUDA(s, cudaGetLastError());
-        slotOf = s->slotOf;
+        rc = ensureSlotOf(s);
+        if (rc) return rc;
+        slotOf = s->slotOf;  // (and it describes the new state as well: body i goes where body i was)
     }
     if (async) {  // pack_vel overwrites the state: everything enqueued on the simulation's stream so far reads the old one
         BH_CUDA(s, cudaEventRecord(s->evStateFree, s->stream));
@@ -793,6 +812,7 @@ static int uploadImpl(Sim *s, const float *const src[7], cudaMemcpyKind kind, bo
     bh::pack_vel_kernel<<<grid, 256, 0, async ? s->upStream : s->stream>>>(dev[3], dev[4], dev[5], s->velacc[0], slotOf, s->n);
     BH_CUDA(s, cudaGetLastError());
     s->placed = true;
+    s->slotOfValid = slotOf != nullptr;  // placed by slotOf[]: it describes the new state as well
     if (async) {
         BH_CUDA(s, cudaEventRecord(s->evPosPacked, s->stream));
         BH_CUDA(s, cudaStreamWaitEvent(s->upStream, s->evPosPacked, 0));  // the staging buffer is free when BOTH packs are done
@@ -1042,9 +1062,8 @@ int bh_read(bh_sim *sim, int32_t which, void *dst, int64_t count) {
 int bh_copy_vertices_device(bh_sim *sim, void *pos4_device, void *vel4_device) {
     BH_ENTER_SETTLED(sim);
     if (!pos4_device && !vel4_device) return BH_OK;
-    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], static_cast<float4 *>(pos4_device),
-                                                                       static_cast<float4 *>(vel4_device), s->n);
-    BH_CUDA(s, cudaGetLastError());
+    int rc = exportVertices(s, static_cast<float4 *>(pos4_device), static_cast<float4 *>(vel4_device));
+    if (rc) return rc;
     return BH_OK;
 }
 
@@ -1062,9 +1081,8 @@ int bh_copy_vertices_async(bh_sim *sim, float *pos4, float *vel4) {
     if (rc) return rc;
     if (s->copyPending) BH_CUDA(s, cudaStreamWaitEvent(s->stream, s->evCopied, 0));  // the staging buffer is still being read
     float4 *dp = s->vtxStaging, *dv = dp + s->n;
-    bh::copy_vertices_kernel<<<(s->n + 255) / 256, 256, 0, s->stream>>>(s->body4[s->cur], s->velacc[s->cur], pos4 ? dp : nullptr,
-                                                                       vel4 ? dv : nullptr, s->n);
-    BH_CUDA(s, cudaGetLastError());
+    rc = exportVertices(s, pos4 ? dp : nullptr, vel4 ? dv : nullptr);
+    if (rc) return rc;
     BH_CUDA(s, cudaEventRecord(s->evExported, s->stream));
     s->deferredPos = pos4;
     s->deferredVel = vel4;
@@ -1133,6 +1151,7 @@ int bh_generate_universe(bh_sim *sim, int32_t kind, uint64_t seed, float p0, flo
     BH_CUDA(s, cudaGetLastError());
     BH_CUDA(s, cudaStreamSynchronize(s->stream));
     s->placed = true;
+    s->slotOfValid = false;
     return BH_OK;
 }
 
