@@ -1465,7 +1465,7 @@ __global__ void adjust_step_kernel(Scalars *sc, int delta) { sc->step += delta; 
 // Small device-side resets as kernels, not cudaMemsetAsync / cudaMemcpyAsync: those may be queued on a copy engine,
 // where they wait behind a bulk host transfer of the asynchronous boundary (measured: ~0.9 ms per step while a
 // 320 MB read-back was in flight).
-__global__ void reset_walk_kernel(Scalars *sc) {
+__global__ void reset_ticket_kernel(Scalars *sc) {
     sc->walkTicket = 0;
     sc->walkSpills = 0;
 }

@@ -224,7 +224,7 @@ void launchWalk(Sim *s, int first, int cnt, bool peers, bool potential = false) 
         const int groups = (cnt + 15) / 16;
         const int grid = std::max(1, std::min(s->walkGrid, (groups + 31) / 32));
         const size_t smem = sizeof(bh::WalkShared);
-        bh::reset_walk_kernel<<<1, 1, 0, s->stream>>>(s->sc);
+        bh::reset_ticket_kernel<<<1, 1, 0, s->stream>>>(s->sc);
         if (potential)
             bh::walk_kernel<false, true><<<grid, bh::kWalkThreads, smem, s->stream>>>(body, s->octet, s->ometa, perm, dst, s->sc, s->spill, s->n, first, cnt, s->eps);
         else if (s->counting)
