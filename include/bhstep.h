@@ -119,7 +119,10 @@ int bh_set_graph(bh_sim *sim, int32_t on);
 
 /* createBuffer(CL_MEM_COPY_HOST_PTR, ...) for the seven generator outputs (GPUBH:155-170):
  * caller-owned host SoA arrays of length nbodies are copied; all other buffers are
- * reset to their initial values (step=-1, maxDepth=1, rest 0). */
+ * reset to their initial values (step=-1, maxDepth=1, rest 0).  Where the bodies are stored is internal: an
+ * upload over an existing state keeps body i in the slot the previous body i had (the last step's tree order), so
+ * a host that sends its bodies every step does not lose the tree stages' locality.  Nothing bh_read or
+ * bh_copy_vertices returns depends on it. */
 int bh_upload(bh_sim *sim, const float *x, const float *y, const float *z, const float *vx, const float *vy,
               const float *vz, const float *mass);
 /* The same without waiting, for pinned host arrays: positions and masses are copied on the simulation's stream, the
