@@ -9,8 +9,11 @@ configs[2] -- seeded Plummer sphere, 10 000 000 bodies, theta = 0.5 -- at every 
 (strong scaling 1/2/4/8), which fits one GPU; `--bodies 1048576` gives configs[1].
 
 `value`      whole-job body-steps/s, state resident in HBM (CUDA events, max over ranks).
-`e2e`        the same step driven through the C ABI with HOST buffers: bh_upload (pinned
-             host -> device) + bh_step + bh_copy_vertices (device -> host) every step.
+`e2e`        the same step driven through the C ABI with HOST buffers: bh_upload_async (pinned
+             host -> device) + bh_step_async + bh_copy_vertices_async (device -> host) every
+             step, wall clock, the last read-back awaited inside the timed region.
+`gpu_launches` stage kernels launched in the timed region (six per step and rank, one more with
+             the peer barrier; the one-thread ticket reset before each walk is not counted).
 `roofline`   the force kernel against the FP32 CUDA-core peak (flops = 20 I + 10 O,
              I/O counted by the instrumented kernel), plus the HBM-bound stages.
 `cpu_baseline` the CPU oracle (port of the reference kernels) on this box's host cores:
