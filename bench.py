@@ -445,7 +445,10 @@ def run_ours(args, rank, world, local_rank):
                             "ffma2_three_register_operands_measured_tflops": x2_rate,
                             "flops_per_launch": flops, "interactions_per_body": inter / n, "opens_per_body": opens / n,
                             "ms_per_launch": f_ms, "share_of_step": f_ms / sum(stage_ms.values()),
-                            "instruction_mix_ceiling": "13 fp32-pipe lane-ops + 1 MUFU per 20 counted flops: at most 0.77 of the FMA peak"}
+                            "instruction_mix_ceiling": "13 fp32-pipe lane-ops + 1 MUFU per 20 counted flops: at most 0.77 of the FMA peak",
+                            # from the committed ncu capture and microbenchmarks (profiles/r2_microbench_fp32x2.txt), not measured in this run
+                            "pipe_cycles_per_child_test": {"fma": 52, "xu": 32, "alu": 28, "issue_slots": 54, "elapsed": 82.6,
+                                                           "note": "per SM sub-partition; no pipe saturated, four in-order warps per sub-partition"}}
         if traffic_note:
             line["roofline"]["traffic_note"] = traffic_note
         kname = {"bounding_box": "bbox_kernel", "build_tree": "build_kernel", "summarize": "summarize_kernel", "sort": "sort_kernel",
